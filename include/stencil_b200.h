@@ -1,0 +1,142 @@
+/*
+ * stencil_b200.h -- C-ABI of the B200-native dispersion-objective library (libstencil_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of Ablinne/optimize-stencil: the objective that
+ * Optimize.optimize() minimises.  The reference has no FFI of its own (it is pure
+ * Python/NumPy); the entry points below are what a ctypes binding placed inside the
+ * reference's extended_stencil/dispersion.py would call instead of its NumPy grid passes.
+ * Citations are file:line into the reference's extended_stencil/ package.
+ *
+ *   sb200_create            <- Dispersion2D.init2 / Dispersion3D.init2   dispersion.py:268-281, 339-357
+ *                              (the caller computes the per-axis tables with NumPy exactly as
+ *                               the reference does and hands them over; the library owns all
+ *                               device memory and never materialises the dense k array)
+ *   sb200_set_weight        <- Dispersion.w / weight.py:4-33             dispersion.py:40
+ *   sb200_objective_batch   <- Dispersion.norm / .stencil_ok / .dt_ok    dispersion.py:235-255, 284-307,
+ *                              for a BATCH of coefficient vectors          360-385, 129-154
+ *                              (replaces the mp.Pool scan, optimize.py:169-190)
+ *   sb200_export            <- Dispersion.omega / .sqrtarg / .sqrtres    dispersion.py:164-196, 309-320,
+ *                                                                         387-399, 111-121
+ *   sb200_destroy, sb200_last_error
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; all floating point is IEEE binary64.
+ *   - every call returns 0 on success, a negative SB200_E* code otherwise; the text is available
+ *     from sb200_last_error().  No C++ exception crosses the ABI.  There is NO CPU fallback:
+ *     without a CUDA device every compute entry point fails with SB200_ECUDA.
+ *   - a context is not re-entrant: one context per host thread.
+ *   - coefficient vectors are in the reference's own field order (stencil.py:209, :275):
+ *       dim 2:  dt, alphax, alphay, betaxy, betayx, deltax, deltay                     (7 doubles)
+ *       dim 3:  dt, alphax, alphay, alphaz, betaxy, betaxz, betayx, betayz, betazx,
+ *               betazy, deltax, deltay, deltaz                                         (13 doubles)
+ *   - the grid is C-ordered with the first axis (x) slowest, like the reference's arrays.
+ *   - results are the UN-GATED grid reductions; the reference's gating (stencil_ok < 0, dt_ok < 0,
+ *     the 1e6 sentinel, the ValueErrors) is applied by the caller from (S, Amin, Amax, nan),
+ *     see SURVEY.md section 8(a) "Gate".
+ *   - results are deterministic: no floating-point atomics, fixed reduction order for a given
+ *     (grid, batch size, x-range).
+ */
+#ifndef STENCIL_B200_H
+#define STENCIL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+/* status codes */
+#define SB200_OK        0
+#define SB200_EINVAL   (-1)  /* bad argument */
+#define SB200_ECUDA    (-2)  /* CUDA runtime error (incl. "no device") */
+#define SB200_ENOMEM   (-3)  /* host or device allocation failed */
+
+/* weight kinds (sb200_set_weight) */
+#define SB200_W_UNIT    0    /* w == 1 everywhere: the reference's default `equal` weight        */
+#define SB200_W_PLANE   1    /* dim 3 only: w[ny*nz], independent of x (weight.py:25-27 shapes)   */
+#define SB200_W_DENSE   2    /* w[nx*ny*nz] (dim 3) or w[nx*ny] (dim 2), C order                  */
+
+/* what sb200_export writes */
+#define SB200_X_OMEGA   0    /* (2/dt) * asin(dt * sqrt(sqrtarg))            dispersion.py:191 */
+#define SB200_X_SQRTARG 1    /* the term under the square root               dispersion.py:319, 398 */
+#define SB200_X_SQRTRES 2    /* sqrt(sqrtarg)                                dispersion.py:116 */
+
+typedef struct sb200_ctx sb200_ctx;
+
+/* Grid description.  Table a (a = 0..dim-1) has n[a] entries:
+ *   cos_kappa[a][i] = cos(kappa_a[i])            dispersion.py:277-278, 351-353
+ *   s2[a][i]        = 0.5*(1 - cos_kappa[a][i])  dispersion.py:279-280, 354-356
+ *   kcomp[a][i]     = kappa_a[i] / (1, Y, Z)[a]  dispersion.py:272-273, 344-346
+ * Y, Z are the cell aspect ratios (Z ignored for dim 2).  `device` is the CUDA ordinal. */
+typedef struct sb200_grid_desc {
+    int32_t dim;
+    int32_t n[3];
+    const double* cos_kappa[3];
+    const double* s2[3];
+    const double* kcomp[3];
+    double Y, Z;
+    int32_t device;
+} sb200_grid_desc;
+
+int sb200_abi_version(void);
+
+/* Number of visible CUDA devices (0 and SB200_ECUDA when there is no usable driver). */
+int sb200_device_count(int32_t* count);
+
+int sb200_create(sb200_ctx** out, const sb200_grid_desc* desc);
+void sb200_destroy(sb200_ctx* ctx);
+
+/* Text of the last error on this context (ctx may be NULL: last error of a failed create). */
+const char* sb200_last_error(const sb200_ctx* ctx);
+
+/* Set the weight function.  `w` is a host pointer (ignored for SB200_W_UNIT) holding `count`
+ * doubles; count must match the kind.  The data is copied to the device. */
+int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, int64_t count);
+
+/* Batched objective.  coeffs: HOST pointer, nbatch rows of ncoef(dim) doubles, row-major.
+ * Only x-planes [x_begin, x_end) of the first axis are visited (k-slab sharding; pass 0, n[0]
+ * for the whole grid).  Outputs are HOST arrays of nbatch entries each:
+ *   S[b]    = sum over the visited points of w * (omega - k)^2       (NaN if any omega is NaN)
+ *   Amin[b] = min sqrtarg, Amax[b] = max sqrtarg  (exact: bitwise the values NumPy's min/max give)
+ *   nan[b]  = number of visited points where omega is NaN
+ * Synchronous: on return the outputs are valid. */
+int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
+                          int32_t x_begin, int32_t x_end,
+                          double* S, double* Amin, double* Amax, int64_t* nan);
+
+/* Same, with DEVICE pointers and an explicit stream (a cudaStream_t passed as void*; NULL = the
+ * context's own stream).  d_coeffs: nbatch*ncoef doubles.  d_out: 4*nbatch doubles laid out as
+ * [S | Amin | Amax | nan-count-as-double].  Asynchronous on `stream`. */
+int sb200_objective_batch_device(sb200_ctx* ctx, const double* d_coeffs, int64_t nbatch,
+                                 int32_t x_begin, int32_t x_end, double* d_out, void* stream);
+
+/* Dense export for ONE coefficient vector over x-planes [x_begin, x_end): writes
+ * (x_end-x_begin)*n[1]*n[2] doubles (C order) to the HOST buffer `out`; also returns the grid
+ * extrema and the NaN count of the exported field (any of the three may be NULL). */
+int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
+                 double* out, double* Amin, double* Amax, int64_t* nan);
+
+/* Same with a DEVICE output buffer and stream; d_stats (may be NULL) receives 3 doubles
+ * [Amin, Amax, nan-count].  coeffs is a HOST pointer (one vector). */
+int sb200_export_device(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
+                        double* d_out, double* d_stats, void* stream);
+
+/* Bookkeeping for benchmarks: kernels launched by this context so far, and the CUDA-event
+ * duration (ms) of the most recent sb200_objective_batch (host-buffer variant). */
+int sb200_launch_count(const sb200_ctx* ctx, int64_t* launches);
+int sb200_last_batch_ms(const sb200_ctx* ctx, double* ms);
+
+/* Tile configuration override for experiments (0 = automatic): candidates per thread (1,2,4,8),
+ * y-tile, x-tile.  Affects only speed and the (deterministic) summation order. */
+int sb200_set_tiling(sb200_ctx* ctx, int32_t cand_per_thread, int32_t tile_y, int32_t tile_x);
+
+/* Register-resident DFMA throughput of `device` in TFLOP/s (2 flop per DFMA), measured with CUDA
+ * events over about `seconds` of back-to-back launches.  The roofline denominator "of measured". */
+int sb200_fp64_peak(int32_t device, double seconds, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STENCIL_B200_H */

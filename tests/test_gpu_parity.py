@@ -1,0 +1,253 @@
+"""GPU parity of the CUDA path (through the C-ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star / SURVEY.md 8d):
+  * objective  |S_gpu - S_ref| / |S_ref| <= 1e-12
+  * omega(k)   max relative error <= 1e-13 (k = 0 excluded where omega = 0: absolute there)
+  * min / max of sqrtarg: BITWISE (they steer SLSQP through stencil_ok / dt_ok)
+Device contract for the extrema: Amin = min(sqrtarg U {+0}), Amax = max(sqrtarg U {+0}); sqrtarg is
+exactly 0 at k = 0, so for any x-range containing plane 0 these are numpy's min / max up to the sign
+of zero.
+"""
+import numpy as np
+import pytest
+
+import np_oracle as O
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_S = 1e-12
+TOL_OMEGA = 1e-13
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import optimize_stencil_b200 as m
+    assert m.device_count() >= 1, "no CUDA device visible"
+    return m
+
+
+def ctx_from_fixture(sb, c):
+    g = c["grid"]
+    dim = c["dim"]
+    return sb.Context(dim, [g["cos"][a] for a in range(dim)], [g["s2"][a] for a in range(dim)],
+                      [g["kcomp"][a] for a in range(dim)], Y=c["Y"], Z=c["Z"])
+
+
+def ctx_from_grid(sb, grid):
+    cos, s2, kc = grid.flat_tables()
+    return sb.Context(grid.dim, cos, s2, kc, Y=grid.Y, Z=grid.Z)
+
+
+def clamp_min(a):
+    return a if a < 0 else 0.0
+
+
+def same_bits(a, b):
+    a, b = np.float64(a), np.float64(b)
+    return (a == b) or (np.isnan(a) and np.isnan(b))
+
+
+def test_golden_cases_objective_and_extrema(sb, golden):
+    """Every fixture case produced by the unmodified reference, fed with the reference's own tables."""
+    checked = 0
+    for i in range(golden.n):
+        c = golden.case(i)
+        if np.any(np.isnan(c["params"])):
+            continue  # NaN parameters never reach the device (dispersion.py:241-243)
+        tag = "case %d %s" % (i, c["tag"])
+        with ctx_from_fixture(sb, c) as ctx:
+            grid = O.Grid(c["dim"], c["N"], c["Y"], c["Z"])
+            w = O.weight(grid, c["wkind"], c["wparams"])
+            if c["wkind"] != "equal":
+                ctx.set_weight(w)
+            S, Amin, Amax, nan = ctx.objective_batch(c["coeffs"])
+            assert same_bits(Amin[0], clamp_min(c["Amin"])), (tag, Amin[0], c["Amin"])
+            assert same_bits(Amax[0], max(c["Amax"], 0.0)), (tag, Amax[0], c["Amax"])
+            if not c["gated"]:
+                assert nan[0] == 0, tag
+                assert relerr(S[0], c["S"]) <= TOL_S, (tag, S[0], c["S"])
+                om, amin2, amax2, nan2 = ctx.export(c["coeffs"], 0)
+                assert same_bits(amin2, Amin[0]) and same_bits(amax2, Amax[0]) and nan2 == 0, tag
+                idx = golden.sample_indices(i, om.size)
+                err = relerr(om.ravel()[idx], c["omega_samples"])
+                assert np.max(err) <= TOL_OMEGA, (tag, np.max(err))
+                if c["omega_full"] is not None:
+                    assert om.shape == c["omega_full"].shape
+                    assert np.max(relerr(om, c["omega_full"])) <= TOL_OMEGA, tag
+                checked += 1
+    assert checked >= 50
+
+
+def test_live_oracle_bitwise_sqrtarg_and_sqrtres(sb):
+    """sqrtarg is evaluated in the reference's operation order: dense export equals NumPy bit for bit."""
+    rng = np.random.default_rng(3)
+    for dim, N, Y, Z, fam in [(3, 33, 1.0, 1.0, "StencilFree3D"), (3, 20, 1.3, 0.7, "StencilFree3D"),
+                              (2, 77, 1.0, 1.0, "StencilFree2D"), (2, 50, 2.0, 1.0, "StencilFree2D")]:
+        grid = O.Grid(dim, N, Y, Z)
+        with ctx_from_grid(sb, grid) as ctx:
+            for _ in range(3):
+                p = 0.1 * rng.standard_normal(len(O.parameter_names(fam)))
+                p[0] = 0.35
+                co = O.coefficients(fam, p)
+                A_ref = O.sqrtarg(grid, co)
+                A, amin, amax, _ = ctx.export(co, 1)
+                np.testing.assert_array_equal(A, A_ref)
+                assert same_bits(amin, clamp_min(A_ref.min())) and same_bits(amax, max(A_ref.max(), 0.0))
+                with np.errstate(invalid="ignore"):
+                    R_ref = np.sqrt(A_ref)
+                R, _, _, nn = ctx.export(co, 2)
+                np.testing.assert_array_equal(R, R_ref)
+                assert nn == np.count_nonzero(np.isnan(R_ref))
+
+
+def test_batch_matches_singles_and_oracle(sb):
+    """A mixed batch (feasible, infeasible, on-CFL) against the oracle's un-gated device contract."""
+    rng = np.random.default_rng(11)
+    grid = O.Grid(3, 40)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    P = [xc + 1e-3 * rng.standard_normal(10) for _ in range(13)]
+    P.append(np.array([0.4, .6, -.5, .4, .3, -.7, .2, .24, -.9, .1]))   # negative sqrtarg
+    P.append(np.array([1.9, 0, 0, 0, 0, 0, 0, 0, 0, 0]))               # dt beyond CFL: s > 1 -> NaNs
+    co = np.stack([O.coefficients("StencilFree3D", p) for p in P])
+    with ctx_from_grid(sb, grid) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        S2, Amin2, Amax2, nan2 = ctx.objective_batch(co)
+        for a, b in ((S, S2), (Amin, Amin2), (Amax, Amax2)):
+            np.testing.assert_array_equal(a, b)  # deterministic
+        np.testing.assert_array_equal(nan, nan2)
+        for b in range(len(P)):
+            Sr, Ar_min, Ar_max, nr = O.device_contract(grid, co[b])
+            assert same_bits(Amin[b], clamp_min(Ar_min)) and same_bits(Amax[b], max(Ar_max, 0.0)), b
+            assert nan[b] == nr, (b, nan[b], nr)
+            if nr == 0:
+                assert relerr(S[b], Sr) <= TOL_S, (b, S[b], Sr)
+            else:
+                assert np.isnan(S[b])
+            s1 = ctx.objective_batch(co[b])
+            assert same_bits(s1[1][0], Amin[b]) and same_bits(s1[2][0], Amax[b]) and s1[3][0] == nan[b]
+            if nr == 0:
+                assert relerr(s1[0][0], S[b]) <= 1e-13
+
+
+@pytest.mark.parametrize("cand,ty,tx", [(1, 8, 1), (2, 16, 3), (4, 64, 7), (8, 32, 2), (4, 256, 64)])
+def test_tilings_agree(sb, cand, ty, tx):
+    """Tile shape only changes the (fixed) summation order: extrema bitwise, S to 1e-13."""
+    rng = np.random.default_rng(5)
+    grid = O.Grid(3, 36, 1.0, 1.0)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    co = np.stack([O.coefficients("StencilFree3D", xc + 1e-3 * rng.standard_normal(10)) for _ in range(7)])
+    with ctx_from_grid(sb, grid) as ctx:
+        ref = ctx.objective_batch(co)
+        ctx.set_tiling(cand, ty, tx)
+        got = ctx.objective_batch(co)
+        np.testing.assert_array_equal(got[1], ref[1])
+        np.testing.assert_array_equal(got[2], ref[2])
+        np.testing.assert_array_equal(got[3], ref[3])
+        assert np.max(relerr(got[0], ref[0])) <= 1e-13
+
+
+def test_weights_plane_and_dense(sb):
+    """weight.py:4-31 shapes: (1,N,N) plane, N^3 dense, (1,N) and (N,N) in 2D."""
+    for dim, N in ((3, 24), (2, 50)):
+        grid = O.Grid(dim, N, 1.2, 0.9)
+        fam = "StencilFree3D" if dim == 3 else "StencilFree2D"
+        p = np.zeros(len(O.parameter_names(fam)))
+        p[0] = 0.3
+        p[-1] = -0.05
+        co = O.coefficients(fam, p)
+        with ctx_from_grid(sb, grid) as ctx:
+            for kind, params in (("xaxis", ()), ("xaxis_soft", ()), ("xaxis_soft", (0.5,)), ("equal", ())):
+                w = O.weight(grid, kind, params)
+                if kind == "equal":
+                    ctx.set_weight_unit()
+                else:
+                    ctx.set_weight(w)
+                S = ctx.objective_batch(co)[0][0]
+                Sr = O.device_contract(grid, co, w)[0]
+                assert relerr(S, Sr) <= TOL_S, (dim, kind, S, Sr)
+            rng = np.random.default_rng(2)
+            w = rng.random(grid.shape)
+            ctx.set_weight(w)
+            assert relerr(ctx.objective_batch(co)[0][0], O.device_contract(grid, co, w)[0]) <= TOL_S
+
+
+def test_x_slabs_partition_the_grid(sb):
+    grid = O.Grid(3, 48)
+    co = O.coefficients("StencilFree3D", [0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    with ctx_from_grid(sb, grid) as ctx:
+        full = ctx.objective_batch(co)
+        cuts = [0, 5, 6, 30, 48]
+        parts = [ctx.objective_batch(co, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert relerr(sum(p[0][0] for p in parts), full[0][0]) <= 1e-13
+        assert same_bits(min(p[1][0] for p in parts), full[1][0])
+        assert same_bits(max(p[2][0] for p in parts), full[2][0])
+        for (a, b), p in zip(zip(cuts[:-1], cuts[1:]), parts):  # each slab against the slab-wise oracle
+            Sr, amin, amax, _ = O.device_contract(O.Grid(3, 48, xslab=(a, b)), co)
+            assert relerr(p[0][0], Sr) <= TOL_S and same_bits(p[2][0], max(amax, 0.0))
+        om = np.concatenate([ctx.export(co, 0, a, b)[0] for a, b in zip(cuts[:-1], cuts[1:])])
+        np.testing.assert_array_equal(om, ctx.export(co, 0)[0])
+
+
+def test_config2_lehe_256(sb, golden):
+    """BASELINE.json configs[1]: calculate_omega.py --lehe --params 0.96 on a 256^3 grid."""
+    c = [golden.case(i) for i in range(golden.n) if golden.case(i)["tag"] == "lehe-3d-256"][0]
+    grid = O.Grid(3, 256)
+    with ctx_from_grid(sb, grid) as ctx:  # tables from this machine's NumPy, as the product does
+        S, Amin, Amax, nan = ctx.objective_batch(c["coeffs"])
+        assert relerr(S[0], c["S"]) <= TOL_S and nan[0] == 0
+        assert relerr(S[0] * O.norm_scale(3, 256), c["norm"]) <= TOL_S
+        om = ctx.export(c["coeffs"], 0)[0]
+        idx = golden.sample_indices(c["id"], om.size)
+        assert np.max(relerr(om.ravel()[idx], c["omega_samples"])) <= TOL_OMEGA
+        ref = O.evaluate(grid, c["coeffs"])  # the full 16.8 M-point field against the live oracle
+        assert np.max(relerr(om, ref["omega"])) <= TOL_OMEGA
+        assert relerr(S[0], ref["S"]) <= TOL_S
+
+
+def test_full_size_512_properties(sb):
+    """BASELINE.json configs[3] grid size (512^3): size-independent properties + a slab-wise oracle."""
+    N = 512
+    grid_tabs = O.Grid(3, 8)  # only to reuse the table code path below
+    x = np.linspace(0, np.pi, N)
+    cos = [np.cos(x)] * 3
+    s2 = [0.5 * (1. - np.cos(x))] * 3
+    rng = np.random.default_rng(0)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    P = [xc + 1e-3 * rng.standard_normal(10) for _ in range(8)]
+    co = np.stack([O.coefficients("StencilFree3D", p) for p in P])
+    with sb.Context(3, cos, s2, [x, x, x]) as ctx:
+        full = ctx.objective_batch(co)
+        assert np.all(full[3] == 0) and np.all(np.isfinite(full[0]))
+        # (1) slabs partition the sum and the extrema
+        halves = [ctx.objective_batch(co, 0, 200), ctx.objective_batch(co, 200, 512)]
+        assert np.max(relerr(halves[0][0] + halves[1][0], full[0])) <= 1e-13
+        np.testing.assert_array_equal(np.maximum(halves[0][2], halves[1][2]), full[2])
+        # (2) a permutation of the axes of a fully anisotropic stencil leaves the objective unchanged
+        #     (x<->y: alphas, deltas and the beta index pairs swap roles)
+        def swap_xy(c):
+            dt, ax, ay, az, bxy, bxz, byx, byz, bzx, bzy, dx_, dy_, dz_ = c
+            return np.array([dt, ay, ax, az, byx, byz, bxy, bxz, bzy, bzx, dy_, dx_, dz_])
+        sw = ctx.objective_batch(np.stack([swap_xy(c) for c in co]))
+        assert np.max(relerr(sw[0], full[0])) <= 1e-12
+        assert np.max(relerr(sw[2], full[2])) <= 1e-15
+        # (3) slab-wise NumPy oracle on three thin slabs of the full-size grid
+        for a, b in ((0, 4), (255, 258), (508, 512)):
+            got = ctx.objective_batch(co[:2], a, b)
+            for j in range(2):
+                Sr, amin, amax, nn = O.device_contract(O.Grid(3, N, xslab=(a, b)), co[j])
+                assert relerr(got[0][j], Sr) <= TOL_S and same_bits(got[2][j], max(amax, 0.0)) and nn == 0
+
+
+def test_argument_errors(sb):
+    grid = O.Grid(2, 16)
+    with ctx_from_grid(sb, grid) as ctx:
+        co = O.coefficients("StencilFree2D", [0.3, 0, 0, 0, 0])
+        with pytest.raises(sb.StencilB200Error):
+            ctx.objective_batch(co, 0, 8)       # x-slabs are a 3-D feature
+        with pytest.raises(ValueError):
+            ctx.objective_batch(np.zeros((2, 13)))
+        with pytest.raises(sb.StencilB200Error):
+            ctx.set_tiling(3, 0, 0)
+    with pytest.raises(sb.StencilB200Error):
+        sb.Context(3, [np.ones(4)] * 3, [np.zeros(4)] * 3, [np.zeros(4)] * 3, device=99)
