@@ -167,8 +167,9 @@ class Context:
         """w: scalar-free array broadcastable to the grid.  Arrays that do not depend on the first
         axis of a 3-D grid go to the device as an (ny, nz) plane; everything else dense."""
         w = np.asarray(w, dtype=np.float64)
-        if self.dim == 3 and w.ndim == 3 and w.shape[0] == 1:
-            plane = _f64(np.broadcast_to(w, (1,) + self.shape[1:])[0])
+        x_independent = w.ndim == 3 and (w.shape[0] == 1 or (w.shape[0] == self.shape[0] and w.strides[0] == 0))
+        if self.dim == 3 and x_independent:
+            plane = _f64(np.broadcast_to(w[:1], (1,) + self.shape[1:])[0])
             self._check(self._lib.sb200_set_weight(self._h, SB200_W_PLANE, _dptr(plane), plane.size), "sb200_set_weight")
         else:
             dense = _f64(np.broadcast_to(w, self.shape))

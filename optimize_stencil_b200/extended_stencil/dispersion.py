@@ -1,0 +1,362 @@
+"""Numerical dispersion relation of a stencil on a dense k-grid -- GPU-backed drop-in for the
+reference's extended_stencil/dispersion.py.
+
+Same public surface (`Dispersion2D(Y, N, stencil)`, `Dispersion3D(Y, Z, N, stencil)`, `norm`,
+`omega`, `stencil_ok`, `dt_ok`, `omega_output`, `omega_spline` / `omega_interp`, the `parameters`,
+`coefficients`, `sqrtarg`, `sqrtres` properties and the table attributes), same sentinel / error
+behaviour (1e6, None, -1, ValueError).  What differs is where the grid arithmetic happens:
+
+  reference: ~25 NumPy passes over N^dim temporaries per norm() call          (dispersion.py:235-255)
+  here:      one fused sm_100a kernel returning (S, Amin, Amax, nan) per coefficient vector, from
+             which norm / stencil_ok / dt_ok / "is omega None" follow on the host ("gate" below).
+
+There is NO CPU fallback: the per-axis tables are NumPy (exactly the reference's init2 formulae),
+every N^dim quantity comes from optimize_stencil_b200._capi.Context, which raises when the CUDA
+library or a device is missing.
+
+Additions that do not exist in the reference:
+  * evaluate_batch / norm_batch: a whole matrix of parameter vectors per launch;
+  * a result cache keyed by the parameter bytes (generalises the one-entry cache at
+    dispersion.py:94-96) plus speculative evaluation of the n forward-difference neighbours SciPy's
+    SLSQP is about to request (same absolute step 1.4901161193847656e-08), so that the objective, both
+    constraints and all their finite-difference Jacobians at one iterate cost ONE launch;
+  * `k` (dense) is built lazily -- the device recomputes k per point and never needs it.
+"""
+import collections
+
+import numpy as np
+import scipy.interpolate as spinterp
+
+from .. import _capi
+
+FD_STEP = 1.4901161193847656e-08   # scipy/optimize/_slsqp_py.py: _epsilon = sqrt(finfo(float).eps)
+
+
+class Dispersion:
+    """Base class; use Dispersion2D or Dispersion3D."""
+
+    dx = 1.0
+    Y = 1.0
+    Z = 1.0
+    dim = 0
+    dt_multiplier = 1.0
+    stencil = None
+    device = 0                 # CUDA ordinal used when the context is (re)created
+    fd_prefetch = True         # evaluate x + h*e_i alongside every cache miss (see module docstring)
+    cache_size = 4096
+
+    def __init__(self, runinit2=True):
+        self._parameters = None
+        self._coefficients = None
+        self._w = 1.0
+        self._w_dirty = True
+        self._ctx = None
+        self._cache = collections.OrderedDict()
+        self._k = None
+        self.init2_run = False
+        self.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
+        if runinit2:
+            self.init2()
+
+    # -- tables (dispersion.py:268-281, 339-357) -------------------------------------------------
+    def init2(self):
+        x = np.linspace(0, np.pi, self.N)
+        self.kappamesh = np.meshgrid(*([x] * self.dim), indexing='ij', sparse=True)
+        scale = (1.0, self.Y, self.Z)
+        self.kmesh = tuple(kap if a == 0 else kap / scale[a] for a, kap in enumerate(self.kappamesh))
+        cos = [np.cos(kap) for kap in self.kappamesh]
+        s2 = [0.5 * (1. - c) for c in cos]
+        for a, name in enumerate('xyz'[:self.dim]):
+            setattr(self, 'kappa' + name, self.kappamesh[a])
+            setattr(self, 'k' + name, self.kmesh[a])
+            setattr(self, 'coskappa' + name, cos[a])
+            setattr(self, 's' + name + '2', s2[a])
+        self.dks = tuple(km.ravel()[1] for km in self.kmesh)
+        self._tables = (cos, s2, list(self.kmesh))
+        self.init2_run = True
+
+    @property
+    def k(self):
+        """|k| on the dense grid (dispersion.py:276, 350).  Built on first use only."""
+        if not self.init2_run:
+            self.init2()
+        if self._k is None:
+            acc = self.kmesh[0] ** 2
+            for km in self.kmesh[1:]:
+                acc = acc + km ** 2
+            self._k = np.sqrt(acc)
+        return self._k
+
+    # -- pickling: the device handle is rebuilt lazily, like the reference's init2 state ----------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_ctx'] = None
+        state['_w_dirty'] = True
+        state['_cache'] = collections.OrderedDict()
+        return state
+
+    # -- weight function ------------------------------------------------------------------------
+    @property
+    def w(self):
+        return self._w
+
+    @w.setter
+    def w(self, value):
+        # The upload is deferred to the next evaluation, so the reference idiom "assign zeros, then
+        # fill in place" (weight.py:8-11) works; call touch_weight() after any LATER in-place edit.
+        self._w = value
+        self.touch_weight()
+
+    def touch_weight(self):
+        """Tell the object that `w` was modified in place: re-upload it and drop cached results."""
+        self._w_dirty = True
+        self._cache.clear()
+
+    # -- device context ---------------------------------------------------------------------------
+    def _context(self):
+        if not self.init2_run:
+            self.init2()
+        if self._ctx is None:
+            cos, s2, kc = self._tables
+            self._ctx = _capi.Context(self.dim, cos, s2, kc, Y=self.Y, Z=self.Z, device=self.device)
+            self._w_dirty = True
+        if self._w_dirty:
+            w = self._w
+            self._w_scale = 1.0
+            if np.ndim(w) == 0:
+                # a scalar weight factors out of the sum; the kernel then runs with unit weights
+                self._ctx.set_weight_unit()
+                self._w_scale = float(w)
+            else:
+                self._ctx.set_weight(np.asarray(w, dtype=float))
+            self._w_dirty = False
+        return self._ctx
+
+    # -- parameters / coefficients (dispersion.py:78-109) ------------------------------------------
+    @property
+    def parameters(self):
+        return self._parameters
+
+    @parameters.setter
+    def parameters(self, parameters):
+        if not self.init2_run:
+            self.init2()
+        if self._parameters is not None and np.all(parameters == self._parameters):
+            return
+        self._parameters = np.array(parameters)   # a copy, like the reference
+        self._coefficients = self.stencil.coefficients(parameters)
+
+    @property
+    def coefficients(self):
+        return self._coefficients
+
+    def _full(self):
+        return np.array(self._coefficients.tolist()[0], dtype=float)
+
+    # -- batched evaluation (new) -----------------------------------------------------------------
+    def _raw_batch(self, P):
+        """(B, dof) parameters -> (S, Amin, Amax, nan) via ONE launch; fills the cache."""
+        ctx = self._context()
+        C = self.stencil.coefficients_batch(P)
+        S, Amin, Amax, nan = ctx.objective_batch(C)
+        self.stats['launches'] += 1
+        self.stats['evaluated'] += len(P)
+        for i in range(len(P)):
+            self._cache[P[i].tobytes()] = (S[i], Amin[i], Amax[i], int(nan[i]), C[i])
+        while len(self._cache) > self.cache_size:
+            self._cache.popitem(last=False)
+        return S, Amin, Amax, nan, C
+
+    def _raw(self, parameters):
+        """Device results for one finite parameter vector, through the cache."""
+        p = np.ascontiguousarray(parameters, dtype=float).ravel()
+        hit = self._cache.get(p.tobytes())
+        if hit is not None:
+            self.stats['hits'] += 1
+            return hit
+        self.stats['misses'] += 1
+        if self.fd_prefetch:
+            # exactly the points scipy's approx_derivative('2-point', abs_step=FD_STEP) will ask for:
+            # x0 + h_vecs[i] with h_vecs = diag(h)  (scipy/optimize/_numdiff.py, _dense_difference)
+            P = np.vstack([p[None, :], p[None, :] + np.diag(np.full(len(p), FD_STEP))])
+        else:
+            P = p[None, :]
+        self._raw_batch(P)
+        return self._cache[p.tobytes()]
+
+    def _gate(self, raw, dtmul=None):
+        """(stencil_ok, dt_ok, usable) from device results -- dispersion.py:284-307 / 360-385, 129-154."""
+        S, Amin, Amax, nan, c = raw
+        if not Amin < 0:                     # also taken when Amin is NaN, as `not a < 0` is
+            sok = self._corner_min(c)
+        else:
+            sok = Amin
+        if np.isnan(sok):
+            raise ValueError("stencil_ok got NaN")
+        if sok < 0:
+            return sok, sok, False
+        with np.errstate(divide='ignore'):
+            dtok = (self.dt_multiplier if dtmul is None else dtmul) / (self.dx * np.sqrt(Amax)) - c[0]
+        if np.isnan(dtok):
+            raise ValueError("dt_ok got NaN")
+        return sok, dtok, not (dtok < 0 or c[0] <= 0)
+
+    def evaluate_batch(self, P):
+        """Rows of free parameters -> dict of arrays norm / stencil_ok / dt_ok (reference semantics,
+        including the 1e6 and -1 sentinels), one launch for all finite rows."""
+        P = np.ascontiguousarray(P, dtype=float)
+        if P.ndim == 1:
+            P = P.reshape(1, -1)
+        B = len(P)
+        out = dict(norm=np.full(B, 1e6), stencil_ok=np.full(B, -1.0), dt_ok=np.full(B, -1.0))
+        ok = ~np.any(np.isnan(P), axis=1)
+        if np.any(ok):
+            S, Amin, Amax, nan, C = self._raw_batch(P[ok])
+            scale = self._norm_scale()
+            for j, i in enumerate(np.flatnonzero(ok)):
+                sok, dtok, usable = self._gate((S[j], Amin[j], Amax[j], nan[j], C[j]))
+                out['stencil_ok'][i], out['dt_ok'][i] = sok, dtok
+                if usable:
+                    if nan[j]:
+                        raise ValueError('Encountered NaNs in omega for params', P[i])
+                    out['norm'][i] = S[j] * self._w_scale * scale
+        return out
+
+    def norm_batch(self, P):
+        return self.evaluate_batch(P)['norm']
+
+    def _norm_scale(self):
+        return (np.pi / (self.N - 1)) ** self.dim * self.Y ** 2 * self.Z ** 2   # dispersion.py:253
+
+    # -- the reference's scalar API ----------------------------------------------------------------
+    def stencil_ok(self, parameters):
+        self.parameters = parameters
+        if np.any(np.isnan(parameters)):
+            return -1
+        return np.array([self._gate(self._raw(parameters))[0]])
+
+    def dt_ok(self, parameters):
+        self.parameters = parameters
+        if np.any(np.isnan(parameters)):
+            return -1.
+        return np.array([self._gate(self._raw(parameters))[1]])
+
+    def omega(self, parameters):
+        """omega(k) on the dense grid, or None when the constraints are violated (dispersion.py:164-196)."""
+        self.parameters = parameters
+        if np.any(np.isnan(parameters)):
+            return None                      # stencil_ok() is -1 for NaN input (dispersion.py:174-178)
+        raw = self._raw(parameters)
+        if not self._gate(raw)[2]:
+            return None
+        om, _, _, nan = self._context().export(raw[4], _capi.SB200_X_OMEGA)
+        if nan:
+            raise ValueError('Encountered NaNs in omega for params', parameters)
+        return om
+
+    def norm(self, parameters):
+        """Weighted squared deviation from omega = k; 1e6 outside the constraints (dispersion.py:235-255)."""
+        if np.any(np.isnan(parameters)):
+            return 1e6
+        self.parameters = parameters
+        raw = self._raw(parameters)
+        if not self._gate(raw)[2]:
+            return 1e6
+        if raw[3]:
+            raise ValueError('Encountered NaNs in omega for params', parameters)
+        return raw[0] * self._w_scale * self._norm_scale()
+
+    @property
+    def sqrtarg(self):
+        return self._context().export(self._full(), _capi.SB200_X_SQRTARG)[0]
+
+    @property
+    def sqrtres(self):
+        res, _, _, nan = self._context().export(self._full(), _capi.SB200_X_SQRTRES)
+        if nan:
+            print('This Function should not have been called')
+            raise ValueError('Got NaNs in sqrt for params {}, stencil_ok {}'.format(
+                self._parameters, self.stencil_ok(self._parameters)))
+        return res
+
+    # -- consumers of the dense omega (dispersion.py:199-232, 322-324, 402-413) --------------------
+    def _group_velocity(self, omega):
+        vgs = np.gradient(omega, *self.dks, edge_order=2)
+        vg = np.sqrt(sum(vgc ** 2 for vgc in vgs))
+        vg[(slice(None, 3),) * self.dim] = 1
+        return vgs, vg
+
+    def omega_output(self, fname, parameters):
+        """gnuplot-style table: one block per kx index, columns kx ky [kz] k omega vph vg vgx vgy [vgz]."""
+        omega = self.omega(parameters)
+        vgs, vg = self._group_velocity(omega)
+        k = self.k
+        with np.errstate(divide='ignore', invalid='ignore'):
+            vph = omega / k
+        vph.ravel()[0] = 1.
+        cols = np.broadcast_arrays(*self.kappamesh, k, omega, vph, vg, *vgs)
+        names = ' '.join('kx ky kz'.split()[:self.dim]) + ' k omega vph vg ' + ' '.join('vgx vgy vgz'.split()[:self.dim])
+        with open(fname, 'wb') as f:
+            f.write(('#' + names + '\n').encode('us-ascii'))
+            for ix in range(omega.shape[0]):
+                np.savetxt(f, np.stack([np.ravel(col[ix]) for col in cols], axis=1))
+                f.write(b'\n')
+
+    def _corner_min(self, c):
+        raise NotImplementedError
+
+
+class Dispersion2D(Dispersion):
+    """Two-dimensional dispersion relation."""
+
+    dim = 2
+
+    def __init__(self, Y, N, stencil, **kwargs):
+        self.Y = Y
+        self.N = N
+        self.stencil = stencil
+        super().__init__(**kwargs)
+
+    def _corner_min(self, c):
+        """sqrtarg at the corners kappa in {0,pi}^2 other than the origin (dispersion.py:294-297)."""
+        dt, ax, ay, bxy, byx, dlx, dly = c
+        Y2 = self.Y ** 2
+        return min((ay + 2 * byx - dly) / Y2,
+                   ax - 2 * bxy - dlx + (ay - 2 * byx - dly) / Y2,
+                   ax + 2 * bxy - dlx)
+
+    def omega_spline(self, parameters, s=0):
+        omega = self.omega(parameters)
+        return spinterp.RectBivariateSpline(self.kx[:, 0], self.ky[0, :], omega, s=s)
+
+
+class Dispersion3D(Dispersion):
+    """Three-dimensional dispersion relation."""
+
+    dim = 3
+
+    def __init__(self, Y, Z, N, stencil, **kwargs):
+        self.Y = Y
+        self.Z = Z
+        self.N = N
+        self.stencil = stencil
+        super().__init__(**kwargs)
+
+    def _corner_min(self, c):
+        """sqrtarg at the seven corners kappa in {0,pi}^3 other than the origin (dispersion.py:369-375)."""
+        dt, ax, ay, az, bxy, bxz, byx, byz, bzx, bzy, dlx, dly, dlz = c
+        Y2, Z2 = self.Y ** 2, self.Z ** 2
+        return min((az + 2.0 * bzx + 2.0 * bzy - dlz) / Z2,
+                   (ay + 2.0 * byx + 2.0 * byz - dly) / Y2,
+                   (ay + 2.0 * byx - 2.0 * byz - dly) / Y2 + (az + 2.0 * bzx - 2.0 * bzy - dlz) / Z2,
+                   ax + 2.0 * bxy + 2.0 * bxz - dlx,
+                   ax + 2.0 * bxy - 2.0 * bxz - dlx + (az - 2.0 * bzx + 2.0 * bzy - dlz) / Z2,
+                   ax - 2.0 * bxy + 2.0 * bxz - dlx + (ay - 2.0 * byx + 2.0 * byz - dly) / Y2,
+                   ax - 2.0 * bxy - 2.0 * bxz - dlx + (ay - 2.0 * byx - 2.0 * byz - dly) / Y2
+                   + (az - 2.0 * bzx - 2.0 * bzy - dlz) / Z2)
+
+    def omega_interp(self, parameters):
+        omega = self.omega(parameters)
+        _, vg = self._group_velocity(omega)
+        axes = (self.kx[:, 0, 0], self.ky[0, :, 0], self.kz[0, 0, :])
+        return spinterp.RegularGridInterpolator(axes, omega), spinterp.RegularGridInterpolator(axes, vg)

@@ -1,0 +1,152 @@
+"""Multi-start SLSQP driver (drop-in for the reference's extended_stencil/optimize.py).
+
+SciPy still drives every search (`scipy.optimize.minimize(method='SLSQP')` with the reference's
+constraints and options, optimize.py:136,142).  What changes is the data-parallel part:
+
+  reference: mp.Pool(nproc).imap(_optimize_single, starts) -- one whole SLSQP run per CPU worker,
+             every objective / constraint call a fresh ~25-pass NumPy sweep (optimize.py:169-190);
+  here:      the searches run in this process against the GPU-backed Dispersion objects.  The start
+             grid is screened in TWO batched launches (CFL time step of every start, then
+             feasibility of every start), and inside each search one launch serves the objective,
+             both constraints and all their finite-difference points of an iterate (see
+             dispersion.py).  `--singlecore` is accepted and changes nothing: there is no pool.
+
+The printed lines keep the reference's format (optimize.py:71, 144, 191, 200-202).
+"""
+import itertools
+import sys
+
+import numpy as np
+import scipy.optimize as scop
+
+from .dispersion import Dispersion2D, Dispersion3D
+from .stencil import get_stencil
+from .weight import weight_functions
+
+
+class make_single_max_constraint:
+    """p[index] <= maxval as an SLSQP 'ineq' function."""
+
+    def __init__(self, index, maxval):
+        self.index, self.maxval = index, maxval
+
+    def __call__(self, p):
+        return self.maxval - p[self.index]
+
+
+class make_single_min_constraint:
+    """p[index] >= minval as an SLSQP 'ineq' function."""
+
+    def __init__(self, index, minval):
+        self.index, self.minval = index, minval
+
+    def __call__(self, p):
+        return p[self.index] - self.minval
+
+
+SLSQP_OPTIONS = dict(disp=False, iprint=2)
+
+
+class Optimize:
+    """Holds the low- and high-resolution dispersion objects and runs the start-grid scan."""
+
+    def __init__(self, args):
+        self.args = args
+        self.dim = args.dim
+        self.div_free = args.div_free
+        self.stencil = get_stencil(args)
+        print('Using stencil', self.stencil.__class__.__name__, 'with free parameters',
+              ", ".join(self.stencil.Parameters._fields))
+
+        def make(N):
+            if self.dim == 2:
+                return Dispersion2D(args.Y, N, self.stencil)
+            return Dispersion3D(args.Y, args.Z, N, self.stencil)
+
+        self.dispersion = make(args.Ngrid_low)
+        self.dispersion_high = self.dispersion if args.Ngrid_high == args.Ngrid_low else make(args.Ngrid_high)
+        for d in {id(self.dispersion): self.dispersion, id(self.dispersion_high): self.dispersion_high}.values():
+            d.dt_multiplier = args.dt_multiplier
+            if args.weight in weight_functions:
+                weight_functions[args.weight](*args.weight_params)(d)
+
+        self.dtmin, self.dtmax = self.args.dtrange[0], self.args.dtrange[1]
+        self.constraints = self._constraint_list(self.dispersion)
+        self.constraints_high = self._constraint_list(self.dispersion_high)
+
+    def _constraint_list(self, dispersion):
+        cons = [dict(type='ineq', fun=dispersion.stencil_ok), dict(type='ineq', fun=dispersion.dt_ok)]
+        for i, fname in enumerate(self.stencil.Parameters._fields):
+            lo, hi = getattr(self.args, fname + 'range')
+            cons.append(dict(type='ineq', fun=make_single_min_constraint(i, lo)))
+            cons.append(dict(type='ineq', fun=make_single_max_constraint(i, hi)))
+        return cons
+
+    # -- one start (optimize.py:115-139) ----------------------------------------------------------
+    def _optimize_single(self, x0):
+        x0 = list(x0)
+        if x0[0] is None:
+            x0[0] = 0
+            dt_ok = np.asarray(self.dispersion.dt_ok(x0)).item()
+            if dt_ok < 0:
+                return x0, None, float('inf')
+            x0[0] = max(min(dt_ok, self.dtmax), self.dtmin)
+        x0 = np.asarray(x0, dtype=float)
+        if self.dispersion.stencil_ok(x0) < 0:
+            return x0, None, float('inf')
+        res = scop.minimize(self.dispersion.norm, x0, method='SLSQP', constraints=self.constraints,
+                            options=dict(SLSQP_OPTIONS))
+        return x0, res, self.dispersion_high.norm(res.x)
+
+    def _optimize_final(self, x0):
+        res = scop.minimize(self.dispersion_high.norm, x0, method='SLSQP', constraints=self.constraints_high,
+                            options=dict(SLSQP_OPTIONS))
+        print('x0={}, x={}, norm={}'.format(x0, res.x, res.fun))
+        return res, res.fun
+
+    # -- the scan (optimize.py:147-205) -----------------------------------------------------------
+    def start_grid(self):
+        """Interior points of an (N+2)-point linspace per parameter; dt scanned or left to the CFL rule."""
+        N = self.args.N
+        axes = []
+        for fname in self.stencil.Parameters._fields[1:]:
+            lo, hi = getattr(self.args, fname + 'range')
+            axes.append(np.linspace(lo, hi, N + 2)[1:-1])
+        dts = np.linspace(self.dtmin, self.dtmax, N + 2)[1:-1] if self.args.scan_dt else [None]
+        return list(itertools.product(dts, *axes))
+
+    def _prescreen(self, starts):
+        """Warm the result cache for the whole start grid with batched launches (replaces the per-start
+        NumPy sweeps the pool workers did first: optimize.py:118-134)."""
+        rows = [[0.0 if v is None else v for v in s] for s in starts]
+        if not rows:
+            return
+        P = np.asarray(rows, dtype=float)
+        first = self.dispersion.evaluate_batch(P)
+        if starts[0][0] is None:   # dt comes from the CFL limit at dt = 0, clipped to dtrange
+            ok = first['dt_ok'] >= 0
+            P = P[ok]
+            P[:, 0] = np.clip(first['dt_ok'][ok], self.dtmin, self.dtmax)
+            if len(P):
+                self.dispersion.evaluate_batch(P)
+
+    def optimize(self):
+        """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
+        starts = self.start_grid()
+        self._prescreen(starts)
+        best = None
+        for x0, res, norm in map(self._optimize_single, starts):
+            print('x0={}, x={}, norm={}'.format(x0, res.x if res else None, norm))
+            sys.stdout.flush()
+            if best is None or norm < best[2]:
+                best = (x0, res, norm)
+        bestx0, bestres, bestnorm = best
+        if self.args.Ngrid_high != self.args.Ngrid_low:
+            print()
+            print('using this result as starting point for high-res optimization:')
+            print('x0={},x={}, norm={}'.format(bestx0, bestres.x, bestnorm))
+            bestres, bestnorm = self._optimize_final(bestres.x)
+        return bestres.x, bestnorm
+
+    def omega_output(self, fname, x):
+        return self.dispersion_high.omega_output(fname, x)

@@ -116,6 +116,24 @@ class Grid:
         self.s2 = tuple(0.5 * (1. - c) for c in self.cos)
         self.shape = self.k.shape
 
+    @classmethod
+    def from_tables(cls, dim, cos, s2, kcomp, Y=1.0, Z=1.0):
+        """A grid built from caller-supplied per-axis tables (what the C-ABI receives)."""
+        g = cls.__new__(cls)
+        g.dim, g.Y, g.Z = dim, Y, (Z if dim == 3 else 1.0)
+        shp = lambda a, t: np.asarray(t, dtype=float).reshape([-1 if i == a else 1 for i in range(dim)])
+        g.cos = tuple(shp(a, cos[a]) for a in range(dim))
+        g.s2 = tuple(shp(a, s2[a]) for a in range(dim))
+        g.kcomp = tuple(shp(a, kcomp[a]) for a in range(dim))
+        g.kappa = None
+        g.N = g.cos[-1].size
+        acc = g.kcomp[0] ** 2
+        for kc in g.kcomp[1:]:
+            acc = acc + kc ** 2
+        g.k = np.sqrt(acc)
+        g.shape = g.k.shape
+        return g
+
     def flat_tables(self):
         """cos / s2 / k-component tables as 1-D arrays per axis (the C-ABI's table inputs)."""
         return ([c.ravel().copy() for c in self.cos], [s.ravel().copy() for s in self.s2],

@@ -1,0 +1,248 @@
+"""The drop-in `extended_stencil` package: same surface and same numbers as the reference.
+
+Every test runs twice: on CPU with the oracle-backed context injected (tests/fake_context.py) to
+check the host logic, and under `-m gpu` against the real CUDA context.  Expected
+values come from the fixtures the unmodified reference produced (oracle/make_golden.py).
+"""
+import itertools
+import pickle
+import types
+
+import numpy as np
+import pytest
+
+import fake_context
+import np_oracle as O
+from conftest import relerr, GOLDEN
+
+
+@pytest.fixture(params=["oracle-backed", pytest.param("cuda", marks=pytest.mark.gpu)])
+def es(request, monkeypatch):
+    """`oracle-backed`: host logic on CPU with tests/fake_context.py injected.
+    `cuda` (-m gpu): the very same assertions against the real sm_100a library."""
+    if request.param == "oracle-backed":
+        fake_context.install(monkeypatch)
+    from optimize_stencil_b200 import extended_stencil
+    return extended_stencil
+
+
+def make_dispersion(es, c):
+    st = getattr(es, c["stencil"])()
+    d = es.Dispersion2D(c["Y"], c["N"], st) if c["dim"] == 2 else es.Dispersion3D(c["Y"], c["Z"], c["N"], st)
+    d.dt_multiplier = c["dtmul"]
+    if c["wkind"] != "equal":
+        es.weight_functions[c["wkind"]](*c["wparams"])(d)
+    return d
+
+
+def check_case(es, c, tol_norm=1e-12):
+    d = make_dispersion(es, c)
+    p = c["params"]
+    tag = "case %d %s" % (c["id"], c["tag"])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sok, dtok, nrm = d.stencil_ok(p), d.dt_ok(p), d.norm(p)
+        om = d.omega(p)
+    assert relerr(np.asarray(sok, dtype=float).ravel()[0], c["stencil_ok"]) <= 1e-14, tag
+    assert abs(np.asarray(dtok, dtype=float).ravel()[0] - c["dt_ok"]) <= 1e-14 * max(1, abs(c["dt_ok"])), tag
+    assert (om is None) == bool(c["gated"]), tag
+    if c["gated"]:
+        assert nrm == 1e6, tag
+    else:
+        assert relerr(nrm, c["norm"]) <= tol_norm, (tag, nrm, c["norm"])
+    return d
+
+
+def test_every_golden_case_through_the_reference_api(es, golden):
+    for i in range(golden.n):
+        c = golden.case(i)
+        if c["N"] > 128 and c["dim"] == 3:
+            continue  # the 256^3 case runs on the GPU (test_gpu_parity.py); too slow for the CPU suite
+        check_case(es, c)
+
+
+def test_surface_matches_reference_names(es):
+    for name in ("Optimize", "Dispersion", "Dispersion2D", "Dispersion3D", "Stencil", "StencilFlags", "namedarray",
+                 "get_stencil", "weight_functions", "minmax", "make_single_max_constraint",
+                 "make_single_min_constraint", "__version__") + tuple(O.STENCILS):
+        assert hasattr(es, name), name
+    d = es.Dispersion3D(1.5, 2.0, 12, es.StencilFree3D())
+    for attr in ("w", "dx", "Y", "Z", "dim", "N", "dt_multiplier", "stencil", "kappamesh", "kappax", "kappay", "kappaz",
+                 "kx", "ky", "kz", "kmesh", "dks", "k", "coskappax", "coskappay", "coskappaz", "sx2", "sy2", "sz2",
+                 "parameters", "coefficients", "init2_run"):
+        assert hasattr(d, attr), attr
+    g = O.Grid(3, 12, 1.5, 2.0)
+    np.testing.assert_array_equal(d.k, g.k)
+    np.testing.assert_array_equal(d.coskappay, g.cos[1])
+    np.testing.assert_array_equal(d.sz2, g.s2[2])
+    assert d.kz.shape == (1, 1, 12) and d.dks == (g.kcomp[0].ravel()[1], g.kcomp[1].ravel()[1], g.kcomp[2].ravel()[1])
+    d2 = es.Dispersion2D(1, 9, es.StencilFree2D())
+    assert d2.Z == 1.0 and d2.k.shape == (9, 9) and d2.w == 1.0
+
+
+def test_sentinels_and_errors(es):
+    d = es.Dispersion2D(1, 20, es.StencilFree2D())
+    nanp = [0.5, np.nan, 0, 0, 0]
+    assert d.norm(nanp) == 1e6 and d.stencil_ok(nanp) == -1 and d.dt_ok(nanp) == -1. and d.omega(nanp) is None
+    assert d.norm([1.5, 0, 0, 0, 0]) == 1e6          # dt beyond CFL
+    assert d.norm([0.0, 0, 0, 0, 0]) == 1e6          # dt <= 0
+    assert d.norm([-.1, 0, 0, 0, 0]) == 1e6
+    d.dt_multiplier = 1.3                              # gate passes with s > 1 -> NaNs in omega -> ValueError
+    with pytest.raises(ValueError):
+        d.norm([0.85, 0, 0, 0, 0])
+    with pytest.raises(ValueError):
+        d.omega([0.85, 0, 0, 0, 0])
+    d.dt_multiplier = 1.0
+    d.parameters = [0.3, 0.3, -0.3, 0.3, 0.7]         # tests/test_dispersion.py:39-47 (bad stencil)
+    assert d.stencil_ok(d.parameters) < 0
+    with pytest.raises(ValueError):
+        d.sqrtres                                      # NaNs in sqrt -> ValueError (dispersion.py:118-120)
+    with pytest.raises(ValueError):
+        es.StencilFree2D().coefficients_batch(np.zeros((2, 3)))
+
+
+def test_parameters_are_copied_and_properties_work(es):
+    d = es.Dispersion3D(1, 1, 10, es.StencilDivFree3D())
+    p = np.array([0.3, -0.10, -0.60, 0.2])            # tests/test_dispersion.py:50-61
+    d.parameters = p
+    p[0] = 9.0
+    assert d.parameters[0] == 0.3
+    assert d.coefficients.shape == (1,) and d.coefficients.deltaz[0] == 0.2
+    g = O.Grid(3, 10)
+    A = O.sqrtarg(g, O.coefficients("StencilDivFree3D", [0.3, -0.10, -0.60, 0.2]))
+    np.testing.assert_array_equal(d.sqrtarg, A)
+    np.testing.assert_array_equal(d.sqrtres, np.sqrt(A))
+    assert d.stencil_ok(d.parameters) > 0 and d.dt_ok(d.parameters) > 0
+    assert not np.any(np.isnan(d.omega(d.parameters)))
+
+
+def test_one_launch_serves_objective_constraints_and_fd_points(es):
+    d = es.Dispersion2D(1, 30, es.StencilSymmetric2D())
+    x = np.array([0.5, 0.05, -0.05, -0.04])
+    d.norm(x)
+    assert d.stats["launches"] == 1 and d.stats["evaluated"] == 5
+    d.stencil_ok(x), d.dt_ok(x)
+    for i in range(4):                                 # scipy's forward-difference points
+        xi = x + np.diag(np.full(4, 1.4901161193847656e-08))[i]
+        d.norm(xi), d.stencil_ok(xi), d.dt_ok(xi)
+    assert d.stats["launches"] == 1 and d.stats["hits"] == 14
+    d.fd_prefetch = False
+    d.norm(x + 1e-3)
+    assert d.stats["launches"] == 2 and d.stats["evaluated"] == 6
+    d.w = 2.0                                          # a new weight invalidates cached sums
+    assert relerr(d.norm(x), 2 * es.Dispersion2D(1, 30, es.StencilSymmetric2D()).norm(x)) < 1e-15
+
+
+def test_batch_api_matches_scalar_api(es):
+    d = es.Dispersion3D(1.2, 0.9, 14, es.StencilFree3D())
+    rng = np.random.default_rng(4)
+    P = 0.08 * rng.standard_normal((12, 10))
+    P[:, 0] = np.linspace(0.1, 1.2, 12)
+    P[3, 4] = np.nan
+    out = d.evaluate_batch(P)
+    launches = d.stats["launches"]
+    assert launches == 1
+    ref = es.Dispersion3D(1.2, 0.9, 14, es.StencilFree3D())
+    for i in range(12):
+        assert out["norm"][i] == ref.norm(P[i])
+        assert out["stencil_ok"][i] == np.asarray(ref.stencil_ok(P[i]), dtype=float).ravel()[0]
+        assert out["dt_ok"][i] == np.asarray(ref.dt_ok(P[i]), dtype=float).ravel()[0]
+    np.testing.assert_array_equal(d.norm_batch(P), out["norm"])
+
+
+def test_pickle_roundtrip_drops_the_device_handle(es):
+    d = es.Dispersion2D(1.0, 25, es.StencilIsotropic2D())
+    es.weight_functions["xaxis_soft"](0.4)(d)
+    x = [0.4, 0.05, -0.03]
+    v = d.norm(x)
+    d2 = pickle.loads(pickle.dumps(d))
+    assert d2._ctx is None and len(d2._cache) == 0
+    assert d2.norm(x) == v
+
+
+def test_weight_shapes_and_values(es):
+    for dim in (2, 3):
+        st = es.StencilFree2D() if dim == 2 else es.StencilFree3D()
+        d = es.Dispersion2D(1.3, 11, st) if dim == 2 else es.Dispersion3D(1.3, 0.7, 11, st)
+        g = O.Grid(dim, 11, 1.3, 0.7)
+        es.weight_functions["xaxis"]()(d)
+        np.testing.assert_array_equal(d.w, O.weight(g, "xaxis"))
+        assert d.w.shape == (11,) * dim
+        es.weight_functions["xaxis_soft"]()(d)
+        np.testing.assert_array_equal(d.w, O.weight(g, "xaxis_soft"))
+        es.weight_functions["xaxis_soft"](0.25)(d)
+        np.testing.assert_array_equal(d.w, O.weight(g, "xaxis_soft", (0.25,)))
+    assert set(es.weight_functions) == {"xaxis", "xaxis_soft"}
+
+
+def test_get_stencil_table(es):
+    """Same selections as the reference for every flag combination (reference tests/test_stencil.py)."""
+    expect = {(2, 0, 0, 0): "StencilFree2D", (2, 0, 0, 1): "StencilIsotropic2D", (2, 0, 1, 0): "StencilSymmetric2D",
+              (2, 0, 1, 1): "StencilIsotropic2D", (2, 1, 0, 0): "StencilDivFree2D",
+              (2, 1, 0, 1): "StencilIsotropicDivFree2D", (2, 1, 1, 0): "StencilIsotropicDivFree2D",
+              (2, 1, 1, 1): "StencilIsotropicDivFree2D",
+              (3, 0, 0, 0): "StencilFree3D", (3, 0, 0, 1): "StencilCylinder3D", (3, 0, 0, 2): "StencilIsotropic3D",
+              (3, 0, 1, 0): "StencilSymmetric3D", (3, 0, 1, 1): None, (3, 0, 1, 2): "StencilIsotropic3D",
+              (3, 1, 0, 0): "StencilDivFree3D", (3, 1, 0, 1): "StencilCylinderDivFree3D",
+              (3, 1, 0, 2): "StencilIsotropicDivFree3D", (3, 1, 1, 0): "StencilIsotropicDivFree3D",
+              (3, 1, 1, 1): None, (3, 1, 1, 2): "StencilIsotropicDivFree3D"}
+    for (dim, df, sb, sa), name in expect.items():
+        a = types.SimpleNamespace(dim=dim, div_free=bool(df), symmetric_beta=bool(sb), symmetric_axes=sa)
+        if name is None:
+            with pytest.raises(NotImplementedError):
+                es.get_stencil(a)
+        else:
+            assert type(es.get_stencil(a)).__name__ == name
+    with pytest.raises(NotImplementedError):
+        es.get_stencil(types.SimpleNamespace(dim=4, div_free=False, symmetric_beta=True, symmetric_axes=0))
+    assert es.StencilIsotropicDivFree3D().dof == 2 and es.StencilFree3D().dof == 10
+    assert es.StencilSymmetric2D().Parameters._fields == ["dt", "betaxy", "deltax", "deltay"]
+
+
+def default_args(**over):
+    base = dict(N=3, scan_dt=True, Ngrid_low=50, Ngrid_high=200, dim=2, div_free=False, symmetric_axes=0,
+                symmetric_beta=True, Y=1.0, Z=1.0, dt_multiplier=1.0, deltaxrange=[-1, 0.25],
+                deltayrange=[-1, 0.25], deltazrange=[-1, 0.25], betaxyrange=[-1, 1], betaxzrange=[-1, 1],
+                betayxrange=[-1, 1], betayzrange=[-1, 1], betazxrange=[-1, 1], betazyrange=[-1, 1],
+                dtrange=[0.1, 1], weight="equal", weight_params=[], singlecore=True)
+    base.update(over)
+    return types.SimpleNamespace(**base)
+
+
+OPT_RUNS = {"divfree": dict(div_free=True, dtrange=[0.6718, 1.0]),
+            "xaxis_soft": dict(weight="xaxis_soft", weight_params=[0.3], N=2),
+            "divfree3d_small": dict(dim=3, div_free=True, dtrange=[0.55, 1.0], Ngrid_low=16, Ngrid_high=24, N=2),
+            "default": {}}
+
+
+def run_optimize(es, name, capsys=None):
+    z = np.load(GOLDEN + "/optimise_runs.npz")
+    opt = es.Optimize(default_args(**OPT_RUNS[name]))
+    assert type(opt.stencil).__name__ == str(z[name + "_stencil"])
+    x, fmin = opt.optimize()
+    # SciPy's ftol is 1e-6: coefficients agree to that tolerance, the minimum far better
+    assert relerr(fmin, z[name + "_norm"]) <= 1e-6, (name, fmin, z[name + "_norm"])
+    assert np.max(np.abs(x - z[name + "_x"])) <= 2e-4, (name, x, z[name + "_x"])
+    return opt, x, fmin, z
+
+
+@pytest.mark.parametrize("name", ["divfree", "xaxis_soft", "divfree3d_small"])
+def test_optimize_matches_reference_result(es, name, capsys):
+    opt, x, fmin, z = run_optimize(es, name)
+    out = capsys.readouterr().out
+    assert out.count("x0=") >= int(z[name + "_nstarts"])   # one line per start (+ the polish line)
+    assert "Using stencil " + str(z[name + "_stencil"]) in out
+    launches = opt.dispersion.stats["launches"]
+    assert launches < opt.dispersion.stats["hits"]          # the cache/prefetch does its job
+
+
+def test_optimize_default_config1(es):
+    """BASELINE.json configs[0]: optimize_stencil.py with no flags (81 starts, N=50 -> 200)."""
+    opt, x, fmin, z = run_optimize(es, "default")
+    assert abs(np.asarray(opt.dispersion_high.dt_ok(x)).ravel()[0] - z["default_dt_ok"][0]) < 1e-5
+
+
+def test_start_grid(es):
+    opt = es.Optimize(default_args(N=2, scan_dt=False))
+    starts = opt.start_grid()
+    assert len(starts) == 8 and starts[0][0] is None
+    assert np.allclose(sorted({s[1] for s in starts}), np.linspace(-1, 1, 4)[1:-1])
