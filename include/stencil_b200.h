@@ -105,7 +105,8 @@ int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, int64_t coun
  *             numpy.min / numpy.max of the reference's array (up to the sign of a zero).  All the
  *             reference needs (dispersion.py:292-302, 149) is "is the minimum negative, and if so
  *             what is it" and the maximum when it is non-negative.  Both are NaN if any sqrtarg is.
- *   nan[b]  = number of visited points where omega is NaN
+ *   nan[b]  = 0 when no visited omega is NaN, a positive number otherwise (sb200_export returns the
+ *             exact count; here it is derived from the partial sums, which a NaN omega poisons)
  * Synchronous: on return the outputs are valid. */
 int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
                           int32_t x_begin, int32_t x_end,

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libstencil_b200.so")
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "csrc", "libstencil_b200.so")  # env: experiments
 
 SB200_W_UNIT, SB200_W_PLANE, SB200_W_DENSE = 0, 1, 2
 SB200_X_OMEGA, SB200_X_SQRTARG, SB200_X_SQRTRES = 0, 1, 2

@@ -247,16 +247,26 @@ struct Plan {
     size_t smem;
 };
 
-size_t smem_bytes(int C, int TY) {
+size_t smem_bytes(int C, int TY, int TZ) {
     const int row = ((2 + 3 * C) + 1) & ~1;  // RowLayout<C>::ROW
-    return (size_t)C * sizeof(Cand) + (size_t)TY * row * 8 + (size_t)TY * 8 + (size_t)C * 8 * 8 * 4;
+    return (size_t)C * sizeof(Cand) + (size_t)TY * row * 8 + (size_t)TY * 8 + (size_t)C * 8 * 8 * 4 +
+           (size_t)C * TZ * 8;
 }
 
 Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
     const GridDev& g = ctx->g;
     Plan p;
     p.C = ctx->force_c ? ctx->force_c : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));
-    p.TZ = std::min(256, ((g.nz + 31) / 32) * 32);
+    if (const char* e = getenv("SB200_FORCE_C")) {         // experiments only
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) p.C = v;
+    }
+    int tz_max = 256;
+    if (const char* e = getenv("SB200_BLOCK_THREADS")) {   // experiments only (tools/sweep.py)
+        const int v = atoi(e);
+        if (v >= 32 && v <= 256 && v % 32 == 0) tz_max = v;
+    }
+    p.TZ = std::min(tz_max, ((g.nz + 31) / 32) * 32);
     p.n_ztiles = (g.nz + p.TZ - 1) / p.TZ;
     p.n_chunks = (B + p.C - 1) / p.C;
     const int ty_max = 256;
@@ -275,7 +285,7 @@ Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
     p.n_xchunks = (nxr + p.TX - 1) / p.TX;
     p.n_ychunks = (g.ny + p.TY - 1) / p.TY;
     p.P = p.n_ztiles * p.n_xchunks * p.n_ychunks;
-    p.smem = smem_bytes(p.C, p.TY);
+    p.smem = smem_bytes(p.C, p.TY, p.TZ);
     return p;
 }
 
