@@ -225,7 +225,12 @@ def run_optimize(es, name, capsys=None):
     # minimum; the coefficients then agree to ~sqrt(ftol / curvature).
     ref = float(z[name + "_norm"])
     assert abs(fmin - ref) <= 1e-6 * max(1.0, abs(ref)), (name, fmin, ref)
-    assert np.max(np.abs(x - z[name + "_x"])) <= 2e-4, (name, x, z[name + "_x"])
+    # ... and OUR objective at the REFERENCE's optimum is the reference's minimum (objective parity there)
+    assert relerr(opt.dispersion_high.norm(z[name + "_x"]), ref) <= 1e-12
+    # "xaxis_soft" ends in a valley whose floor is flat to 1e-6 over ~1e-3 in delta_y: coefficients are
+    # only determined to that width there; the well-conditioned runs agree to ~1e-4.
+    xtol = 5e-3 if name == "xaxis_soft" else 2e-4
+    assert np.max(np.abs(x - z[name + "_x"])) <= xtol, (name, x, z[name + "_x"])
     return opt, x, fmin, z
 
 
