@@ -249,8 +249,9 @@ struct Plan {
 
 size_t smem_bytes(int C, int TY, int TZ) {
     const int row = ((2 + 3 * C) + 1) & ~1;  // RowLayout<C>::ROW
-    return (size_t)C * sizeof(Cand) + (size_t)TY * row * 8 + (size_t)TY * 8 + (size_t)C * 8 * 8 * 4 +
-           (size_t)C * TZ * 8;
+    const int nwarps = (TZ + 31) / 32;
+    (void)TY;                                // tables are per warp (32 rows), not per y tile
+    return (size_t)C * sizeof(Cand) + (size_t)nwarps * 32 * row * 8 + (size_t)C * 8 * 8 * 4 + (size_t)C * TZ * 8;
 }
 
 Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
@@ -269,8 +270,7 @@ Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
     p.TZ = std::min(tz_max, ((g.nz + 31) / 32) * 32);
     p.n_ztiles = (g.nz + p.TZ - 1) / p.TZ;
     p.n_chunks = (B + p.C - 1) / p.C;
-    const int ty_max = 256;
-    p.TY = ctx->force_ty ? std::min(ctx->force_ty, g.ny) : std::min(g.ny, ty_max);
+    p.TY = ctx->force_ty ? std::min(ctx->force_ty, g.ny) : g.ny;
     p.TX = ctx->force_tx ? std::min(ctx->force_tx, nxr) : nxr;
     // Enough CTAs for ~16 waves of (2 CTAs x SMs) when the problem is that large; never below 8
     // k-points of work per thread and candidate.
@@ -281,7 +281,7 @@ Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
     if (!ctx->force_tx)
         while (ctas() < target && p.TX > 1) p.TX = (p.TX + 1) / 2;
     if (!ctx->force_ty)
-        while (ctas() < target && p.TY > 8) p.TY = (p.TY + 1) / 2;
+        while (ctas() < target && p.TY > 32) p.TY = ((p.TY + 1) / 2 + 31) / 32 * 32;   // whole 32-row tiles
     p.n_xchunks = (nxr + p.TX - 1) / p.TX;
     p.n_ychunks = (g.ny + p.TY - 1) / p.TY;
     p.P = p.n_ztiles * p.n_xchunks * p.n_ychunks;
