@@ -22,8 +22,6 @@ Additions that do not exist in the reference:
     constraints and all their finite-difference Jacobians at one iterate cost ONE launch;
   * `k` (dense) is built lazily -- the device recomputes k per point and never needs it.
 """
-import collections
-
 import numpy as np
 import scipy.interpolate as spinterp
 
@@ -51,7 +49,7 @@ class Dispersion:
         self._w = 1.0
         self._w_dirty = True
         self._ctx = None
-        self._cache = collections.OrderedDict()
+        self._cache = {}
         self._k = None
         self.init2_run = False
         self.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
@@ -92,7 +90,7 @@ class Dispersion:
         state = self.__dict__.copy()
         state['_ctx'] = None
         state['_w_dirty'] = True
-        state['_cache'] = collections.OrderedDict()
+        state['_cache'] = {}
         return state
 
     # -- weight function ------------------------------------------------------------------------
@@ -141,65 +139,86 @@ class Dispersion:
     def parameters(self, parameters):
         if not self.init2_run:
             self.init2()
-        if self._parameters is not None and np.all(parameters == self._parameters):
-            return
-        self._parameters = np.array(parameters)   # a copy, like the reference
-        self._coefficients = self.stencil.coefficients(parameters)
+        self._parameters = np.array(parameters)   # a copy, like the reference (dispersion.py:98-99)
+        self._coefficients = None                 # the record array is built when somebody asks for it
 
     @property
     def coefficients(self):
+        if self._coefficients is None and self._parameters is not None:
+            self._coefficients = self.stencil.coefficients(self._parameters)
         return self._coefficients
 
     def _full(self):
-        return np.array(self._coefficients.tolist()[0], dtype=float)
+        return np.array(self.coefficients.tolist()[0], dtype=float)
 
     # -- batched evaluation (new) -----------------------------------------------------------------
+    # cache entry: [S, Amin, Amax, nan, full coefficient row, gate]; gate = (dt_multiplier, stencil_ok,
+    # dt_ok, usable) is filled on first use, because its ValueErrors must surface only for points a
+    # caller actually asked about (prefetched finite-difference neighbours may be garbage).
     def _raw_batch(self, P):
-        """(B, dof) parameters -> (S, Amin, Amax, nan) via ONE launch; fills the cache."""
+        """(B, dof) parameters -> (S, Amin, Amax, nan, C) via ONE launch; fills the cache."""
         ctx = self._context()
         C = self.stencil.coefficients_batch(P)
         S, Amin, Amax, nan = ctx.objective_batch(C)
         self.stats['launches'] += 1
         self.stats['evaluated'] += len(P)
+        cache = self._cache
+        if len(cache) + len(P) > self.cache_size:
+            for key in list(cache)[:len(cache) // 2 + len(P)]:   # drop the oldest half
+                del cache[key]
+        Sl, lo, hi, nl = S.tolist(), Amin.tolist(), Amax.tolist(), nan.tolist()
         for i in range(len(P)):
-            self._cache[P[i].tobytes()] = (S[i], Amin[i], Amax[i], int(nan[i]), C[i])
-        while len(self._cache) > self.cache_size:
-            self._cache.popitem(last=False)
+            cache[P[i].tobytes()] = [Sl[i], lo[i], hi[i], nl[i], C[i], None]
         return S, Amin, Amax, nan, C
 
-    def _raw(self, parameters):
-        """Device results for one finite parameter vector, through the cache."""
-        p = np.ascontiguousarray(parameters, dtype=float).ravel()
-        hit = self._cache.get(p.tobytes())
-        if hit is not None:
+    def _entry(self, parameters):
+        """Cache entry of one parameter vector (evaluating it if needed); None for NaN input."""
+        p = parameters
+        if type(p) is not np.ndarray or p.dtype != np.float64 or p.ndim != 1 or not p.flags.c_contiguous:
+            p = np.ascontiguousarray(parameters, dtype=float).ravel()
+        key = p.tobytes()
+        e = self._cache.get(key)
+        if e is not None:
             self.stats['hits'] += 1
-            return hit
+            return e
+        if np.isnan(p).any():
+            return None
         self.stats['misses'] += 1
         if self.fd_prefetch:
             # exactly the points scipy's approx_derivative('2-point', abs_step=FD_STEP) will ask for:
             # x0 + h_vecs[i] with h_vecs = diag(h)  (scipy/optimize/_numdiff.py, _dense_difference)
             P = np.vstack([p[None, :], p[None, :] + np.diag(np.full(len(p), FD_STEP))])
         else:
-            P = p[None, :]
+            P = p[None, :].copy()
         self._raw_batch(P)
-        return self._cache[p.tobytes()]
+        return self._cache[key]
 
-    def _gate(self, raw, dtmul=None):
-        """(stencil_ok, dt_ok, usable) from device results -- dispersion.py:284-307 / 360-385, 129-154."""
-        S, Amin, Amax, nan, c = raw
+    def _raw(self, parameters):
+        return self._entry(parameters)
+
+    def _gate(self, e):
+        """(stencil_ok, dt_ok, usable) of a cache entry -- dispersion.py:284-307 / 360-385, 129-154."""
+        g = e[5]
+        if g is not None and g[0] == self.dt_multiplier:
+            return g[1], g[2], g[3]
+        S, Amin, Amax, nan, c = e[0], e[1], e[2], e[3], e[4]
         if not Amin < 0:                     # also taken when Amin is NaN, as `not a < 0` is
             sok = self._corner_min(c)
         else:
             sok = Amin
-        if np.isnan(sok):
+        if sok != sok:
             raise ValueError("stencil_ok got NaN")
         if sok < 0:
-            return sok, sok, False
-        with np.errstate(divide='ignore'):
-            dtok = (self.dt_multiplier if dtmul is None else dtmul) / (self.dx * np.sqrt(Amax)) - c[0]
-        if np.isnan(dtok):
-            raise ValueError("dt_ok got NaN")
-        return sok, dtok, not (dtok < 0 or c[0] <= 0)
+            dtok, usable = sok, False
+        else:
+            dt = float(c[0])
+            root = self.dx * float(np.sqrt(Amax))
+            dtok = (self.dt_multiplier / root if root != 0.0 else float('inf')) - dt
+            if dtok != dtok:
+                raise ValueError("dt_ok got NaN")
+            usable = not (dtok < 0 or dt <= 0)
+        e[5] = (self.dt_multiplier, sok, dtok, usable)
+        return sok, dtok, usable
 
     def evaluate_batch(self, P):
         """Rows of free parameters -> dict of arrays norm / stencil_ok / dt_ok (reference semantics,
@@ -211,15 +230,17 @@ class Dispersion:
         out = dict(norm=np.full(B, 1e6), stencil_ok=np.full(B, -1.0), dt_ok=np.full(B, -1.0))
         ok = ~np.any(np.isnan(P), axis=1)
         if np.any(ok):
-            S, Amin, Amax, nan, C = self._raw_batch(P[ok])
-            scale = self._norm_scale()
+            Pok = np.ascontiguousarray(P[ok])
+            self._raw_batch(Pok)
+            scale = self._norm_scale() * self._w_scale
             for j, i in enumerate(np.flatnonzero(ok)):
-                sok, dtok, usable = self._gate((S[j], Amin[j], Amax[j], nan[j], C[j]))
+                e = self._cache[Pok[j].tobytes()]
+                sok, dtok, usable = self._gate(e)
                 out['stencil_ok'][i], out['dt_ok'][i] = sok, dtok
                 if usable:
-                    if nan[j]:
+                    if e[3]:
                         raise ValueError('Encountered NaNs in omega for params', P[i])
-                    out['norm'][i] = S[j] * self._w_scale * scale
+                    out['norm'][i] = e[0] * scale
         return out
 
     def norm_batch(self, P):
@@ -231,40 +252,42 @@ class Dispersion:
     # -- the reference's scalar API ----------------------------------------------------------------
     def stencil_ok(self, parameters):
         self.parameters = parameters
-        if np.any(np.isnan(parameters)):
+        e = self._entry(parameters)
+        if e is None:
             return -1
-        return np.array([self._gate(self._raw(parameters))[0]])
+        return np.array([self._gate(e)[0]])
 
     def dt_ok(self, parameters):
         self.parameters = parameters
-        if np.any(np.isnan(parameters)):
+        e = self._entry(parameters)
+        if e is None:
             return -1.
-        return np.array([self._gate(self._raw(parameters))[1]])
+        return np.array([self._gate(e)[1]])
 
     def omega(self, parameters):
         """omega(k) on the dense grid, or None when the constraints are violated (dispersion.py:164-196)."""
         self.parameters = parameters
-        if np.any(np.isnan(parameters)):
+        e = self._entry(parameters)
+        if e is None:
             return None                      # stencil_ok() is -1 for NaN input (dispersion.py:174-178)
-        raw = self._raw(parameters)
-        if not self._gate(raw)[2]:
+        if not self._gate(e)[2]:
             return None
-        om, _, _, nan = self._context().export(raw[4], _capi.SB200_X_OMEGA)
+        om, _, _, nan = self._context().export(e[4], _capi.SB200_X_OMEGA)
         if nan:
             raise ValueError('Encountered NaNs in omega for params', parameters)
         return om
 
     def norm(self, parameters):
         """Weighted squared deviation from omega = k; 1e6 outside the constraints (dispersion.py:235-255)."""
-        if np.any(np.isnan(parameters)):
+        e = self._entry(parameters)
+        if e is None:
             return 1e6
         self.parameters = parameters
-        raw = self._raw(parameters)
-        if not self._gate(raw)[2]:
+        if not self._gate(e)[2]:
             return 1e6
-        if raw[3]:
+        if e[3]:
             raise ValueError('Encountered NaNs in omega for params', parameters)
-        return raw[0] * self._w_scale * self._norm_scale()
+        return np.float64(e[0] * self._w_scale * self._norm_scale())   # numpy scalar, as f.sum() gives
 
     @property
     def sqrtarg(self):
