@@ -251,3 +251,87 @@ def test_argument_errors(sb):
             ctx.set_tiling(3, 0, 0)
     with pytest.raises(sb.StencilB200Error):
         sb.Context(3, [np.ones(4)] * 3, [np.zeros(4)] * 3, [np.zeros(4)] * 3, device=99)
+
+
+@pytest.mark.parametrize("dim,N", [(3, 1), (3, 2), (3, 5), (3, 31), (3, 33), (3, 65), (2, 1), (2, 2), (2, 3), (2, 257), (2, 300)])
+def test_ragged_and_tiny_grids(sb, dim, N):
+    """Grid sizes that do not fill warps, 32-row tiles or z tiles; N = 1 is the origin alone."""
+    fam = "StencilFree3D" if dim == 3 else "StencilFree2D"
+    rng = np.random.default_rng(N)
+    P = 0.05 * rng.standard_normal((3, len(O.parameter_names(fam))))
+    P[:, 0] = [0.2, 0.45, 0.6]
+    if N == 1:
+        x = np.array([0.0])
+        tabs = ([np.cos(x)] * dim, [0.5 * (1. - np.cos(x))] * dim, [x] * dim)
+        grid = O.Grid.from_tables(dim, *tabs)
+    else:
+        grid = O.Grid(dim, N)
+        tabs = grid.flat_tables()
+    co = np.stack([O.coefficients(fam, p) for p in P])
+    with sb.Context(dim, *tabs) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        for b in range(3):
+            Sr, amin, amax, nr = O.device_contract(grid, co[b])
+            assert same_bits(Amin[b], clamp_min(amin)) and same_bits(Amax[b], max(amax, 0.0)), (N, b)
+            assert (nan[b] > 0) == (nr > 0)
+            if nr == 0:
+                assert (S[b] == Sr == 0.0) or relerr(S[b], Sr) <= TOL_S, (N, b, S[b], Sr)
+        om = ctx.export(co[0], 0)[0]
+        with np.errstate(invalid="ignore"):
+            ref = O.omega_from_sqrtarg(np.broadcast_to(O.sqrtarg(grid, co[0]), grid.shape), co[0][0])
+        assert np.max(relerr(om, ref)) <= TOL_OMEGA
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 7, 8, 9, 63, 64, 65, 130])
+def test_batch_sizes_and_padding(sb, B):
+    """Batches that do not fill a candidate chunk; both the zero-copy (B <= 64) and the staged path."""
+    rng = np.random.default_rng(B)
+    grid = O.Grid(3, 20)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    co = np.stack([O.coefficients("StencilFree3D", xc + 2e-3 * rng.standard_normal(10)) for _ in range(B)])
+    with ctx_from_grid(sb, grid) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        pick = sorted(set([0, B // 2, B - 1]))
+        for b in pick:
+            Sr, amin, amax, nr = O.device_contract(grid, co[b])
+            assert relerr(S[b], Sr) <= TOL_S and same_bits(Amax[b], amax) and nan[b] == 0
+        one = np.array([ctx.objective_batch(co[b])[0][0] for b in pick])
+        assert np.max(relerr(one, S[pick])) <= 1e-13
+
+
+def test_nan_and_inf_coefficients_do_not_poison_neighbours(sb):
+    """A NaN / inf coefficient row yields NaN for that row only (the host gate never sends NaN parameters,
+    but the C-ABI must not trap on them)."""
+    grid = O.Grid(3, 18)
+    good = O.coefficients("StencilFree3D", [0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    bad1, bad2 = good.copy(), good.copy()
+    bad1[5] = np.nan
+    bad2[10] = np.inf
+    co = np.stack([good, bad1, good, bad2, good])
+    with ctx_from_grid(sb, grid) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        assert S[0] == S[2] == S[4] and np.isfinite(S[0]) and nan[0] == 0
+        assert np.isnan(S[1]) and np.isnan(Amin[1]) and np.isnan(Amax[1]) and nan[1] > 0
+        assert np.isnan(S[3]) and nan[3] > 0
+        assert relerr(S[0], O.device_contract(grid, good)[0]) <= TOL_S
+
+
+def test_config3_scan_grid(sb):
+    """BASELINE.json configs[2] in miniature: the --div-free 3-D family (dt, deltax), a dt x deltax start
+    grid in ONE launch, including gated candidates, against the oracle looped over the same points."""
+    grid = O.Grid(3, 40)
+    dts = np.linspace(0.40, 0.80, 10)[1:-1]     # straddles the 3-D CFL limit of this family
+    dls = np.linspace(-0.3, 0.25, 10)[1:-1]
+    P = np.array([(a, b) for a in dts for b in dls])
+    co = np.stack([O.coefficients("StencilIsotropicDivFree3D", p) for p in P])
+    with ctx_from_grid(sb, grid) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+    gated = 0
+    for b in range(len(P)):
+        r = O.evaluate(grid, co[b])
+        assert same_bits(Amin[b], clamp_min(r["Amin"])) and same_bits(Amax[b], max(r["Amax"], 0.0)), b
+        if r["omega"] is None:
+            gated += 1
+        else:
+            assert relerr(S[b], r["S"]) <= TOL_S and nan[b] == 0, b
+    assert 0 < gated < len(P)
