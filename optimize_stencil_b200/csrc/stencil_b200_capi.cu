@@ -397,9 +397,18 @@ extern "C" int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64
     const double evals = (double)B * (double)(xe - xb) * ctx->g.ny * ctx->g.nz;
     if (B <= 64 && evals < 67108864.0) {
         // Latency path (SciPy's SLSQP asks for one iterate and its finite-difference neighbours at a
-        // time): the kernel reads the coefficients from, and writes the results to, pinned host
-        // memory directly (unified addressing) -- one launch and one stream sync, no copy calls.
-        if ((rc = objective_device_impl(ctx, ctx->h_pin, B, xb, xe, h_out, ctx->stream))) return rc;
+        // time): no event records and no D2H copy call -- the last CTA of each candidate chunk writes
+        // the 4 results straight into pinned host memory (unified addressing).  With few CTAs the
+        // coefficients are read from pinned host memory as well (one launch + one sync in total);
+        // with many CTAs each of them would cross PCIe, so they are copied to the device first.
+        const Plan p = make_plan(ctx, B, xe - xb);
+        const double* d_in = ctx->h_pin;
+        if (p.n_chunks * p.n_ztiles * p.n_xchunks * p.n_ychunks > 64) {
+            if ((rc = grow(ctx, &ctx->d_coeffs, &ctx->d_coeffs_cap, nc))) return rc;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coeffs, ctx->h_pin, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            d_in = ctx->d_coeffs;
+        }
+        if ((rc = objective_device_impl(ctx, d_in, B, xb, xe, h_out, ctx->stream))) return rc;
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->last_ms = 0.0;
     } else {

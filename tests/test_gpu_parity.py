@@ -335,3 +335,23 @@ def test_config3_scan_grid(sb):
         else:
             assert relerr(S[b], r["S"]) <= TOL_S and nan[b] == 0, b
     assert 0 < gated < len(P)
+
+
+def test_config5_grid_2048_slabs(sb):
+    """BASELINE.json configs[4] grid size (2048^3, 8.6e9 k-points, not representable in the reference):
+    x-slabs partition the sum and the extrema; thin slabs agree with the slab-wise oracle."""
+    N = 2048
+    x = np.linspace(0, np.pi, N)
+    cos, s2 = np.cos(x), 0.5 * (1. - np.cos(x))
+    co = O.coefficients("StencilFree3D", [0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    with sb.Context(3, [cos] * 3, [s2] * 3, [x] * 3) as ctx:
+        full = ctx.objective_batch(co)
+        assert full[3][0] == 0 and np.isfinite(full[0][0])
+        cuts = [0, 256, 1024, 1027, 2048]          # the 8-GPU slab size, a big one, a ragged one
+        parts = [ctx.objective_batch(co, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert relerr(sum(p[0][0] for p in parts), full[0][0]) <= 1e-13
+        assert same_bits(max(p[2][0] for p in parts), full[2][0])
+        for a, b in ((0, 1), (1024, 1026), (2047, 2048)):
+            got = ctx.objective_batch(co, a, b)
+            Sr, amin, amax, nn = O.device_contract(O.Grid(3, N, xslab=(a, b)), co)
+            assert relerr(got[0][0], Sr) <= TOL_S and same_bits(got[2][0], max(amax, 0.0)) and nn == 0

@@ -1,0 +1,41 @@
+"""Dense omega export (sb200::export_kernel): device-side throughput against the HBM-write roofline.
+
+    python tools/export_bench.py [N]     (3-D N^3 grid, Lehe dt = 0.96; default N = 512 -> 1 GiB of omega)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import optimize_stencil_b200 as sb  # noqa: E402
+from optimize_stencil_b200.extended_stencil import StencilSymmetric3D  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+x = np.linspace(0, np.pi, N)
+cos, s2 = np.cos(x), 0.5 * (1. - np.cos(x))
+ctx = sb.Context(3, [cos] * 3, [s2] * 3, [x] * 3)
+dlx = 0.25 * (1 - 1 / 0.96 ** 2 * np.sin(np.pi * 0.96 / 2.0))
+co = StencilSymmetric3D().coefficients_batch([0.96, .125, .125, .125, dlx, 0, 0])[0]
+out = torch.empty(N ** 3, dtype=torch.float64, device="cuda")
+stats = torch.empty(3, dtype=torch.float64, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+hbm = peaks.get("hbm_gbs", 6650.0)
+for what, name in ((0, "omega"), (1, "sqrtarg"), (2, "sqrtres")):
+    for _ in range(3):
+        ctx.export_device(co, out.data_ptr(), what, d_stats_ptr=stats.data_ptr(), stream=st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    K = 10
+    for _ in range(K):
+        ctx.export_device(co, out.data_ptr(), what, d_stats_ptr=stats.data_ptr(), stream=st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    gbs = N ** 3 * 8 / (ms * 1e-3) / 1e9
+    print("export %-8s %d^3: %.3f ms  %.1f GB/s written (algorithmic 8 B/point)  %.2f of %s HBM copy peak %.0f GB/s  "
+          "%.1f G points/s" % (name, N, ms, gbs, gbs / hbm, "measured" if peaks else "fallback", hbm, N ** 3 / ms / 1e6))

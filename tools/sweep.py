@@ -23,7 +23,13 @@ cos = np.cos(x)
 s2 = 0.5 * (1. - cos)
 rng = np.random.default_rng(0)
 xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
-P = xc + 1e-3 * rng.standard_normal((B, 10))
+if os.environ.get("SWEEP_CASE") == "lehe":   # near-CFL stencil: most points in the HIGH class
+    dlx = 0.25 * (1 - 1 / 0.96 ** 2 * np.sin(np.pi * 0.96 / 2.0))
+    xc = np.array([0.96, .125, .125, .125, .125, .125, .125, dlx, 0.0, 0.0])
+    P = xc + 1e-5 * rng.standard_normal((B, 10))
+    P[:, 0] = 0.96 - 1e-4 * rng.random(B)
+else:
+    P = xc + 1e-3 * rng.standard_normal((B, 10))
 co = np.zeros((B, 13))
 co[:, 0] = P[:, 0]
 co[:, 4:10] = P[:, 1:7]
@@ -41,8 +47,10 @@ for (c, ty, tx) in configs:
     ctx.objective_batch(co[:8])  # warm-up
     best = 1e30
     for rep in range(3):
+        t0 = time.perf_counter()
         out = ctx.objective_batch(co)
-        best = min(best, ctx.last_batch_ms)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        best = min(best, ctx.last_batch_ms or wall_ms)   # the zero-copy latency path records no events
     if ref is None:
         ref = out
     dev = float(np.max(np.abs(out[0] - ref[0]) / np.abs(ref[0])))
