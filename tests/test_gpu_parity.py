@@ -355,3 +355,23 @@ def test_config5_grid_2048_slabs(sb):
             got = ctx.objective_batch(co, a, b)
             Sr, amin, amax, nn = O.device_contract(O.Grid(3, N, xslab=(a, b)), co)
             assert relerr(got[0][0], Sr) <= TOL_S and same_bits(got[2][0], max(amax, 0.0)) and nn == 0
+
+
+def test_full_size_512_against_the_c_oracle(sb):
+    """BASELINE.json configs[3] at its full grid size: whole-grid sums and extrema of several candidates
+    against the plain-C oracle (compensated summation, libm sqrt/asin) -- no sampling, all 134 M k-points."""
+    import c_oracle
+    N = 512
+    x = np.linspace(0, np.pi, N)
+    cos, s2 = np.cos(x), 0.5 * (1. - np.cos(x))
+    rng = np.random.default_rng(0)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    P = xc + 1e-3 * rng.standard_normal((6, 10))        # the first candidates of bench.py's batch
+    co = np.stack([O.coefficients("StencilFree3D", p) for p in P])
+    ref = c_oracle.COracle(3, [cos] * 3, [s2] * 3, [x] * 3).objective(co[:3])
+    with sb.Context(3, [cos] * 3, [s2] * 3, [x] * 3) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        assert np.all(nan == 0)
+        for b in range(3):
+            assert relerr(S[b], ref[0][b]) <= TOL_S, (b, S[b], ref[0][b])
+            assert same_bits(Amax[b], ref[2][b]) and same_bits(Amin[b], clamp_min(ref[1][b]))
