@@ -69,7 +69,10 @@ typedef struct sb200_ctx sb200_ctx;
  *   cos_kappa[a][i] = cos(kappa_a[i])            dispersion.py:277-278, 351-353
  *   s2[a][i]        = 0.5*(1 - cos_kappa[a][i])  dispersion.py:279-280, 354-356
  *   kcomp[a][i]     = kappa_a[i] / (1, Y, Z)[a]  dispersion.py:272-273, 344-346
- * Y, Z are the cell aspect ratios (Z ignored for dim 2).  `device` is the CUDA ordinal. */
+ * Y, Z are the cell aspect ratios (Z ignored for dim 2).  Y2, Z2 are the divisors (Y*dx)**2 and
+ * (Z*dx)**2 of dispersion.py:319, 398 EXACTLY as the caller's host language evaluated them -- NumPy's
+ * and libm's x**2 is not always the correctly rounded x*x, and sqrtarg must divide by the same bits.
+ * Pass 0 to let the library use Y*Y and Z*Z.  `device` is the CUDA ordinal. */
 typedef struct sb200_grid_desc {
     int32_t dim;
     int32_t n[3];
@@ -77,6 +80,7 @@ typedef struct sb200_grid_desc {
     const double* s2[3];
     const double* kcomp[3];
     double Y, Z;
+    double Y2, Z2;
     int32_t device;
 } sb200_grid_desc;
 

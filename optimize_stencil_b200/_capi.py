@@ -31,7 +31,8 @@ class _GridDesc(ctypes.Structure):
                 ("cos_kappa", ctypes.POINTER(ctypes.c_double) * 3),
                 ("s2", ctypes.POINTER(ctypes.c_double) * 3),
                 ("kcomp", ctypes.POINTER(ctypes.c_double) * 3),
-                ("Y", ctypes.c_double), ("Z", ctypes.c_double), ("device", ctypes.c_int32)]
+                ("Y", ctypes.c_double), ("Z", ctypes.c_double), ("Y2", ctypes.c_double), ("Z2", ctypes.c_double),
+                ("device", ctypes.c_int32)]
 
 
 _lib = None
@@ -132,6 +133,10 @@ class Context:
             shape.append(tabs[0].shape[0])
             d.cos_kappa[a], d.s2[a], d.kcomp[a] = (_dptr(t) for t in tabs)
         d.Y, d.Z, d.device = float(Y), float(Z), int(device)
+        # the divisors of dispersion.py:319, 398 with the caller's own types: `**2` on a Python float or a
+        # NumPy scalar is libm/NumPy pow, which is not always the correctly rounded Y*Y
+        dx = 1.0
+        d.Y2, d.Z2 = float((Y * dx) ** 2), float((Z * dx) ** 2)
         self.shape = tuple(shape)
         rc = self._lib.sb200_create(ctypes.byref(self._h), ctypes.byref(d))
         if rc != 0:

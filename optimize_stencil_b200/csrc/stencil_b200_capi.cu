@@ -153,10 +153,13 @@ static int create_impl(sb200_ctx* ctx, const sb200_grid_desc* d) {
     g.cx = T + offs[0]; g.cy = T + offs[1]; g.cz = T + offs[2];
     g.sx2 = T + offs[3]; g.sy2 = T + offs[4]; g.sz2 = T + offs[5];
     g.kx2 = T + offs[6]; g.ky2 = T + offs[7]; g.kz2 = T + offs[8];
-    // (Y*dx)**2 with dx = 1.0 (dispersion.py:319, 398); pow(v, 2) == v*v exactly.
-    const double Y2 = (d->Y * 1.0) * (d->Y * 1.0), Z2 = (d->Z * 1.0) * (d->Z * 1.0);
+    // (Y*dx)**2 with dx = 1.0 (dispersion.py:319, 398), preferably the caller's own bits (see the header).
+    const double Y2 = d->Y2 > 0 ? d->Y2 : (d->Y * 1.0) * (d->Y * 1.0);
+    const double Z2 = d->Z2 > 0 ? d->Z2 : (d->Z * 1.0) * (d->Z * 1.0);
     if (d->dim == 3) { g.Y2 = Y2; g.Z2 = Z2; }
     else             { g.Y2 = 1.0; g.Z2 = Y2; }
+    g.rY2 = 1.0 / g.Y2;   // IEEE division on the host: the correctly rounded reciprocals div_invariant needs
+    g.rZ2 = 1.0 / g.Z2;
     ctx->unit_cell = (g.Y2 == 1.0 && g.Z2 == 1.0);
     g.w = nullptr;
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -375,3 +375,29 @@ def test_full_size_512_against_the_c_oracle(sb):
         for b in range(3):
             assert relerr(S[b], ref[0][b]) <= TOL_S, (b, S[b], ref[0][b])
             assert same_bits(Amax[b], ref[2][b]) and same_bits(Amin[b], clamp_min(ref[1][b]))
+
+
+def test_non_unit_cells_divide_exactly(sb):
+    """sqrtarg divides by (Y dx)^2 and (Z dx)^2 (dispersion.py:398).  The kernels use a 5-instruction
+    invariant-divisor division; it must round exactly like numpy's true division, also for awkward
+    divisors (mantissa of all ones, powers of two, tiny, huge)."""
+    rng = np.random.default_rng(42)
+    cells = [(1.25, 0.8), (np.sqrt(2 - 2 ** -52), 3.0), (0.5, 4.0), (1 / 3, 7 / 3), (1e-3, 1e3),
+             (np.nextafter(1.0, 2.0), np.nextafter(1.0, 0.0)), (np.pi, np.e)]
+    cells += [tuple(np.exp(rng.uniform(-2, 2, 2))) for _ in range(8)]
+    for Y, Z in cells:
+        grid = O.Grid(3, 24, Y, Z)
+        with ctx_from_grid(sb, grid) as ctx:
+            for _ in range(2):
+                p = 0.1 * rng.standard_normal(10)
+                p[0] = 0.3
+                co = O.coefficients("StencilFree3D", p)
+                A_ref = O.sqrtarg(grid, co)
+                A = ctx.export(co, 1)[0]
+                np.testing.assert_array_equal(A, A_ref)
+                r = ctx.objective_batch(co)
+                assert same_bits(r[1][0], clamp_min(A_ref.min())) and same_bits(r[2][0], max(A_ref.max(), 0.0)), (Y, Z)
+        grid2 = O.Grid(2, 40, Y)
+        with ctx_from_grid(sb, grid2) as ctx:
+            co = O.coefficients("StencilFree2D", [0.3, 0.05, -0.04, -0.02, 0.03])
+            np.testing.assert_array_equal(ctx.export(co, 1)[0], O.sqrtarg(grid2, co))

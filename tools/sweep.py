@@ -40,7 +40,12 @@ co[:, 3] = 1.0 - 2.0 * co[:, 8] - 2.0 * co[:, 9] - 3.0 * co[:, 12]
 
 peak = sb.fp64_peak_tflops(0, 0.5)
 print("measured DFMA peak %.2f TFLOP/s (nominal 37.2)" % peak, flush=True)
-ctx = sb.Context(3, [cos] * 3, [s2] * 3, [x] * 3)
+YY, ZZ = float(os.environ.get("SWEEP_Y", 1.0)), float(os.environ.get("SWEEP_Z", 1.0))
+ctx = sb.Context(3, [cos] * 3, [s2] * 3, [x, x / YY, x / ZZ], Y=YY, Z=ZZ)
+if os.environ.get("SWEEP_W") == "plane":
+    ctx.set_weight(np.exp(-(x[None, :, None] / 0.3) ** 2 - (x[None, None, :] / 0.3) ** 2))
+elif os.environ.get("SWEEP_W") == "dense":
+    ctx.set_weight(np.random.default_rng(1).random((N, N, N)))
 ref = None
 for (c, ty, tx) in configs:
     ctx.set_tiling(c, ty, tx)
