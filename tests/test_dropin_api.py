@@ -227,10 +227,15 @@ def run_optimize(es, name, capsys=None):
     assert abs(fmin - ref) <= 1e-6 * max(1.0, abs(ref)), (name, fmin, ref)
     # ... and OUR objective at the REFERENCE's optimum is the reference's minimum (objective parity there)
     assert relerr(opt.dispersion_high.norm(z[name + "_x"]), ref) <= 1e-12
-    # "xaxis_soft" ends in a valley whose floor is flat to 1e-6 over ~1e-3 in delta_y: coefficients are
-    # only determined to that width there; the well-conditioned runs agree to ~1e-4.
-    xtol = 5e-3 if name == "xaxis_soft" else 2e-4
-    assert np.max(np.abs(x - z[name + "_x"])) <= xtol, (name, x, z[name + "_x"])
+    # The well-conditioned runs agree to ~1e-4 in every coefficient.  "xaxis_soft" weights only a narrow
+    # band around the kx axis, so delta_y barely enters the objective: the valley floor is flat to 1e-6
+    # over ~1e-2 in delta_y (two runs differing in the 16th digit of the objective stop 1e-2 apart
+    # there); dt, beta_xy and delta_x are still determined to ~1e-3.
+    dx_ = np.abs(x - z[name + "_x"])
+    if name == "xaxis_soft":
+        assert np.max(dx_[:3]) <= 2e-3 and dx_[3] <= 0.1, (name, x, z[name + "_x"])
+    else:
+        assert np.max(dx_) <= 2e-4, (name, x, z[name + "_x"])
     return opt, x, fmin, z
 
 
