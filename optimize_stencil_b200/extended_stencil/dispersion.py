@@ -30,6 +30,15 @@ from .. import _capi
 FD_STEP = 1.4901161193847656e-08   # scipy/optimize/_slsqp_py.py: _epsilon = sqrt(finfo(float).eps)
 
 
+def _python_min(columns):
+    """Element-wise equivalent of Python's min() over a list (the reference calls min(b) on its corner
+    list): keep the first entry unless a later one is strictly smaller -- NaNs behave as they do there."""
+    best = columns[0]
+    for col in columns[1:]:
+        best = np.where(col < best, col, best)
+    return best
+
+
 class Dispersion:
     """Base class; use Dispersion2D or Dispersion3D."""
 
@@ -222,25 +231,40 @@ class Dispersion:
 
     def evaluate_batch(self, P):
         """Rows of free parameters -> dict of arrays norm / stencil_ok / dt_ok (reference semantics,
-        including the 1e6 and -1 sentinels), one launch for all finite rows."""
+        including the 1e6 and -1 sentinels), one launch for all finite rows.  Gating is vectorised;
+        batches of up to `cache_size`/4 rows also warm the per-point cache of the scalar API."""
         P = np.ascontiguousarray(P, dtype=float)
         if P.ndim == 1:
             P = P.reshape(1, -1)
         B = len(P)
         out = dict(norm=np.full(B, 1e6), stencil_ok=np.full(B, -1.0), dt_ok=np.full(B, -1.0))
         ok = ~np.any(np.isnan(P), axis=1)
-        if np.any(ok):
-            Pok = np.ascontiguousarray(P[ok])
-            self._raw_batch(Pok)
-            scale = self._norm_scale() * self._w_scale
-            for j, i in enumerate(np.flatnonzero(ok)):
-                e = self._cache[Pok[j].tobytes()]
-                sok, dtok, usable = self._gate(e)
-                out['stencil_ok'][i], out['dt_ok'][i] = sok, dtok
-                if usable:
-                    if e[3]:
-                        raise ValueError('Encountered NaNs in omega for params', P[i])
-                    out['norm'][i] = e[0] * scale
+        if not np.any(ok):
+            return out
+        Pok = np.ascontiguousarray(P[ok])
+        if len(Pok) * 4 <= self.cache_size:
+            S, Amin, Amax, nan, C = self._raw_batch(Pok)
+        else:
+            C = self.stencil.coefficients_batch(Pok)
+            S, Amin, Amax, nan = self._context().objective_batch(C)
+            self.stats['launches'] += 1
+            self.stats['evaluated'] += len(Pok)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            corner = self._corner_min_batch(C)
+            sok = np.where(Amin < 0, Amin, corner)          # `a if a < 0 else min(b)`, NaN-transparent
+            if np.any(np.isnan(sok)):
+                raise ValueError("stencil_ok got NaN")
+            dtok = self.dt_multiplier / (self.dx * np.sqrt(Amax)) - C[:, 0]
+            dtok = np.where(sok < 0, sok, dtok)
+            if np.any(np.isnan(dtok)):
+                raise ValueError("dt_ok got NaN")
+        usable = ~((sok < 0) | (dtok < 0) | (C[:, 0] <= 0))
+        if np.any(usable & (nan > 0)):
+            raise ValueError('Encountered NaNs in omega for params', Pok[np.flatnonzero(usable & (nan > 0))[0]])
+        idx = np.flatnonzero(ok)
+        out['stencil_ok'][idx] = sok
+        out['dt_ok'][idx] = dtok
+        out['norm'][idx] = np.where(usable, S * (self._w_scale * self._norm_scale()), 1e6)
         return out
 
     def norm_batch(self, P):
@@ -348,6 +372,12 @@ class Dispersion2D(Dispersion):
                    ax - 2 * bxy - dlx + (ay - 2 * byx - dly) / Y2,
                    ax + 2 * bxy - dlx)
 
+    def _corner_min_batch(self, C):
+        dt, ax, ay, bxy, byx, dlx, dly = C.T
+        Y2 = self.Y ** 2
+        b = [(ay + 2 * byx - dly) / Y2, ax - 2 * bxy - dlx + (ay - 2 * byx - dly) / Y2, ax + 2 * bxy - dlx]
+        return _python_min(b)
+
     def omega_spline(self, parameters, s=0):
         omega = self.omega(parameters)
         return spinterp.RectBivariateSpline(self.kx[:, 0], self.ky[0, :], omega, s=s)
@@ -377,6 +407,19 @@ class Dispersion3D(Dispersion):
                    ax - 2.0 * bxy + 2.0 * bxz - dlx + (ay - 2.0 * byx + 2.0 * byz - dly) / Y2,
                    ax - 2.0 * bxy - 2.0 * bxz - dlx + (ay - 2.0 * byx - 2.0 * byz - dly) / Y2
                    + (az - 2.0 * bzx - 2.0 * bzy - dlz) / Z2)
+
+    def _corner_min_batch(self, C):
+        dt, ax, ay, az, bxy, bxz, byx, byz, bzx, bzy, dlx, dly, dlz = C.T
+        Y2, Z2 = self.Y ** 2, self.Z ** 2
+        b = [(az + 2.0 * bzx + 2.0 * bzy - dlz) / Z2,
+             (ay + 2.0 * byx + 2.0 * byz - dly) / Y2,
+             (ay + 2.0 * byx - 2.0 * byz - dly) / Y2 + (az + 2.0 * bzx - 2.0 * bzy - dlz) / Z2,
+             ax + 2.0 * bxy + 2.0 * bxz - dlx,
+             ax + 2.0 * bxy - 2.0 * bxz - dlx + (az - 2.0 * bzx + 2.0 * bzy - dlz) / Z2,
+             ax - 2.0 * bxy + 2.0 * bxz - dlx + (ay - 2.0 * byx + 2.0 * byz - dly) / Y2,
+             ax - 2.0 * bxy - 2.0 * bxz - dlx + (ay - 2.0 * byx - 2.0 * byz - dly) / Y2
+             + (az - 2.0 * bzx - 2.0 * bzy - dlz) / Z2]
+        return _python_min(b)
 
     def omega_interp(self, parameters):
         omega = self.omega(parameters)

@@ -9,11 +9,17 @@ constraints and options, optimize.py:136,142).  What changes is the data-paralle
              grid is screened in TWO batched launches (CFL time step of every start, then
              feasibility of every start), and inside each search one launch serves the objective,
              both constraints and all their finite-difference points of an iterate (see
-             dispersion.py).  `--singlecore` is accepted and changes nothing: there is no pool.
+             dispersion.py).  `--singlecore` is accepted and changes nothing by default.
+             What remains is SciPy's own per-iteration Python overhead; for big start grids it can be
+             spread over worker processes that share the GPU (`args.workers = N` or the environment
+             variable OPTSTENCIL_WORKERS=N; every worker re-creates its device context lazily, exactly
+             like the reference's pickled Dispersion objects re-run init2).  Each start is independent
+             and deterministic, so the result does not depend on the number of workers.
 
 The printed lines keep the reference's format (optimize.py:71, 144, 191, 200-202).
 """
 import itertools
+import os
 import sys
 
 import numpy as np
@@ -133,13 +139,25 @@ class Optimize:
     def optimize(self):
         """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
         starts = self.start_grid()
-        self._prescreen(starts)
+        workers = int(getattr(self.args, 'workers', 0) or os.environ.get('OPTSTENCIL_WORKERS', 0) or 0)
+        pool = None
+        if workers > 1 and len(starts) >= 2 * workers and not getattr(self.args, 'singlecore', False):
+            import multiprocessing as mp
+            method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')   # never fork a live CUDA context
+            pool = mp.get_context(method).Pool(workers)
+            results = pool.imap(self._optimize_single, starts, chunksize=max(1, len(starts) // (8 * workers)))
+        else:
+            self._prescreen(starts)
+            results = map(self._optimize_single, starts)
         best = None
-        for x0, res, norm in map(self._optimize_single, starts):
+        for x0, res, norm in results:
             print('x0={}, x={}, norm={}'.format(x0, res.x if res else None, norm))
             sys.stdout.flush()
             if best is None or norm < best[2]:
                 best = (x0, res, norm)
+        if pool is not None:
+            pool.close()
+            pool.join()
         bestx0, bestres, bestnorm = best
         if self.args.Ngrid_high != self.args.Ngrid_low:
             print()

@@ -262,3 +262,26 @@ def test_start_grid(es):
     starts = opt.start_grid()
     assert len(starts) == 8 and starts[0][0] is None
     assert np.allclose(sorted({s[1] for s in starts}), np.linspace(-1, 1, 4)[1:-1])
+
+
+def test_worker_processes_give_the_same_answer(monkeypatch, capsys):
+    """The optional process pool (args.workers) only spreads SciPy's Python overhead: same starts, same
+    deterministic searches, same result.  CPU variant: fork, so that the oracle-backed context is inherited."""
+    fake_context.install(monkeypatch)
+    monkeypatch.setenv("OPTSTENCIL_START_METHOD", "fork")
+    from optimize_stencil_b200 import extended_stencil as es
+    over = dict(div_free=True, dtrange=[0.6718, 1.0], Ngrid_low=30, Ngrid_high=30, N=4)
+    x1, f1 = es.Optimize(default_args(**over)).optimize()
+    x2, f2 = es.Optimize(default_args(workers=2, singlecore=False, **over)).optimize()
+    assert f1 == f2 and np.array_equal(x1, x2)
+    assert capsys.readouterr().out.count("x0=") == 2 * 16
+
+
+@pytest.mark.gpu
+def test_worker_processes_on_the_gpu(capsys):
+    """Same with real spawned workers, each creating its own CUDA context on the shared GPU."""
+    from optimize_stencil_b200 import extended_stencil as es
+    over = dict(div_free=True, dtrange=[0.6718, 1.0], Ngrid_low=30, Ngrid_high=30, N=4)
+    x1, f1 = es.Optimize(default_args(**over)).optimize()
+    x2, f2 = es.Optimize(default_args(workers=2, singlecore=False, **over)).optimize()
+    assert f1 == f2 and np.array_equal(x1, x2)
