@@ -141,9 +141,12 @@ class Optimize:
         starts = self.start_grid()
         workers = int(getattr(self.args, 'workers', 0) or os.environ.get('OPTSTENCIL_WORKERS', 0) or 0)
         pool = None
+        method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')       # never fork a live CUDA context
+        if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
+            print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
+            workers = 0
         if workers > 1 and len(starts) >= 2 * workers and not getattr(self.args, 'singlecore', False):
             import multiprocessing as mp
-            method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')   # never fork a live CUDA context
             pool = mp.get_context(method).Pool(workers)
             results = pool.imap(self._optimize_single, starts, chunksize=max(1, len(starts) // (8 * workers)))
         else:
