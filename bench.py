@@ -200,6 +200,8 @@ def run_gpu_arm(a):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     N, B = a.grid, a.batch
