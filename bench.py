@@ -199,9 +199,12 @@ def run_gpu_arm(a):
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (a.gpus, world))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # Keep stdout to the one JSON line: anything libraries print while the communicator comes up (NCCL's
+    # version banner, debug output) is sent to stderr until the warm-up is over.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     N, B = a.grid, a.batch
@@ -225,6 +228,9 @@ def run_gpu_arm(a):
     for _ in range(a.warmup):
         out = sharded.evaluate(coeffs_dev)
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
