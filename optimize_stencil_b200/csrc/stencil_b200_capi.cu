@@ -350,6 +350,7 @@ static int objective_device_impl(sb200_ctx* ctx, const double* d_coeffs, int64_t
         rc = grow(ctx, &ctx->d_tickets, &ctx->d_tickets_cap, (size_t)p.n_chunks);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_tickets, 0, ctx->d_tickets_cap * sizeof(unsigned int), st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));   // rare (growth only): later calls may come on another stream
     }
     BatchArgs a;
     a.coeffs = d_coeffs; a.ncoef = ctx->ncoef; a.B = B; a.x_begin = xb; a.x_end = xe;
