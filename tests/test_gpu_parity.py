@@ -401,3 +401,52 @@ def test_non_unit_cells_divide_exactly(sb):
         with ctx_from_grid(sb, grid2) as ctx:
             co = O.coefficients("StencilFree2D", [0.3, 0.05, -0.04, -0.02, 0.03])
             np.testing.assert_array_equal(ctx.export(co, 1)[0], O.sqrtarg(grid2, co))
+
+
+def test_fuzz_against_the_c_oracle(sb):
+    """Differential fuzzing: random grids, cells, families, weights and parameter vectors (many of them
+    infeasible: negative sqrtarg, s > 1, tiny and huge dt) against the plain-C oracle -- every class of
+    the omega evaluation, every reduction path, the gate inputs bitwise."""
+    import c_oracle
+    rng = np.random.default_rng(20260101)
+    fams = sorted(O.STENCILS)
+    n_omega = 0
+    for it in range(120):
+        fam = fams[it % len(fams)]
+        dim = O.STENCILS[fam][0]
+        N = int(rng.integers(2, 41 if dim == 3 else 160))
+        Y, Z = (1.0, 1.0) if it % 3 else (float(np.exp(rng.uniform(-1, 1))), float(np.exp(rng.uniform(-1, 1))))
+        grid = O.Grid(dim, N, Y, Z)
+        cos, s2, kc = grid.flat_tables()
+        dof = len(O.parameter_names(fam))
+        B = int(rng.integers(1, 10))
+        P = rng.uniform(-0.4, 0.4, (B, dof)) * rng.choice([0.05, 0.3, 1.0], (B, 1))
+        P[:, 0] = rng.choice([0.01, 0.2, 0.5, 0.9, 1.3], B) * rng.uniform(0.8, 1.2, B)
+        co = np.stack([O.coefficients(fam, p) for p in P])
+        w = None
+        if it % 4 == 1:
+            w = rng.random((1,) + grid.shape[1:]) if dim == 3 else rng.random(grid.shape)
+        elif it % 4 == 2:
+            w = rng.random(grid.shape)
+        ref = c_oracle.COracle(dim, cos, s2, kc, Y, Z, w)
+        Sr, lo, hi, nr = ref.objective(co)
+        with sb.Context(dim, cos, s2, kc, Y=Y, Z=Z) as ctx:
+            if w is not None:
+                ctx.set_weight(w)
+            S, Amin, Amax, nan = ctx.objective_batch(co)
+            for b in range(B):
+                tag = (it, fam, N, Y, Z, b, P[b])
+                assert same_bits(Amin[b], clamp_min(lo[b])) and same_bits(Amax[b], max(hi[b], 0.0)), tag
+                assert (nan[b] > 0) == (nr[b] > 0), tag
+                if nr[b] == 0:
+                    assert (S[b] == 0.0 == Sr[b]) or relerr(S[b], Sr[b]) <= TOL_S, tag + (S[b], Sr[b])
+                else:
+                    assert np.isnan(S[b]), tag
+            if it % 5 == 0:
+                om = ctx.export(co[0], 0)[0]
+                want = ref.export(co[0], 0)
+                both_nan = np.isnan(om) & np.isnan(want)
+                assert np.array_equal(np.isnan(om), np.isnan(want)), (it, fam)
+                assert np.max(np.where(both_nan, 0.0, relerr(om, want))) <= TOL_OMEGA, (it, fam)
+                n_omega += 1
+    assert n_omega >= 20
