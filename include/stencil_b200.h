@@ -17,6 +17,8 @@
  *                              (replaces the mp.Pool scan, optimize.py:169-190)
  *   sb200_export            <- Dispersion.omega / .sqrtarg / .sqrtres    dispersion.py:164-196, 309-320,
  *                                                                         387-399, 111-121
+ *   sb200_group_velocity    <- Dispersion.omega_output / omega_interp    dispersion.py:199-232, 402-413
+ *                              (numpy.gradient of omega, |vg|, vph, k on the device)
  *   sb200_destroy, sb200_last_error
  *
  * Conventions
@@ -133,6 +135,18 @@ int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_b
  * receives 3 doubles [Amin, Amax, nan-count].  coeffs is a HOST pointer (one vector). */
 int sb200_export_device(sb200_ctx* ctx, const double* coeffs, int32_t what, int32_t x_begin, int32_t x_end,
                         double* d_out, double* d_stats, void* stream);
+
+/* Group-velocity fields of ONE coefficient vector on the whole grid -- what Dispersion.omega_output and
+ * Dispersion3D.omega_interp derive from omega (dispersion.py:208-220, 408-410):
+ *   omega                                    prod(n) doubles
+ *   vgc[a] = numpy.gradient(omega, *h, edge_order=2)[a]   dim arrays of prod(n), concatenated; h[a] = dks[a]
+ *   vg     = sqrt(sum_a vgc[a]^2)            (the caller applies the reference's vg[:3,:3(,:3)] = 1 patch)
+ *   vph    = omega / k                       (k = 0 at the origin gives NaN, as in NumPy; the caller sets it to 1)
+ *   k      = sqrt(sum_a kcomp[a]^2)
+ * in NumPy's own arithmetic (bit-identical to numpy.gradient on the exported omega).  Every output is a
+ * HOST buffer or NULL.  Needs n[a] >= 3 on every axis (numpy.gradient's own requirement). */
+int sb200_group_velocity(sb200_ctx* ctx, const double* coeffs, const double* h,
+                         double* omega, double* vgc, double* vg, double* vph, double* k, int64_t* nan);
 
 /* The context's own (non-blocking) stream as a cudaStream_t, for callers of the *_device variants. */
 int sb200_get_stream(const sb200_ctx* ctx, void** stream);

@@ -18,7 +18,7 @@ SB200_X_OMEGA, SB200_X_SQRTARG, SB200_X_SQRTRES = 0, 1, 2
 EXPORTED_SYMBOLS = (
     "sb200_abi_version", "sb200_device_count", "sb200_create", "sb200_destroy", "sb200_last_error",
     "sb200_set_weight", "sb200_objective_batch", "sb200_objective_batch_device", "sb200_export",
-    "sb200_export_device", "sb200_get_stream", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling", "sb200_fp64_peak",
+    "sb200_export_device", "sb200_group_velocity", "sb200_get_stream", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling", "sb200_fp64_peak",
 )
 
 
@@ -63,6 +63,7 @@ def load_library():
     lib.sb200_objective_batch_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp]
     lib.sb200_export.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, dp, dp, dp, i64p]
     lib.sb200_export_device.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
+    lib.sb200_group_velocity.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, i64p]
     lib.sb200_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     lib.sb200_launch_count.argtypes = [vp, i64p]
     lib.sb200_last_batch_ms.argtypes = [vp, dp]
@@ -217,6 +218,22 @@ class Context:
                                     ctypes.byref(amin), ctypes.byref(amax), ctypes.byref(nan))
         self._check(rc, "sb200_export")
         return out, amin.value, amax.value, nan.value
+
+    def group_velocity(self, coeffs, spacings, want=("omega", "vgc", "vg", "vph", "k")):
+        """omega, numpy.gradient(omega, *spacings, edge_order=2), |vg|, vph = omega/k and k on the device;
+        returns a dict of host arrays (vgc: tuple of `dim` arrays) plus 'nan' (NaN count of omega)."""
+        c = _f64(coeffs, (self.ncoef,))
+        h = _f64(np.asarray(spacings, dtype=float), (self.dim,))
+        bufs = {name: np.empty(((self.dim,) if name == "vgc" else ()) + self.shape) for name in want}
+        ptr = lambda name: _dptr(bufs[name]) if name in bufs else None
+        nan = ctypes.c_int64()
+        rc = self._lib.sb200_group_velocity(self._h, _dptr(c), _dptr(h), ptr("omega"), ptr("vgc"), ptr("vg"), ptr("vph"),
+                                            ptr("k"), ctypes.byref(nan))
+        self._check(rc, "sb200_group_velocity")
+        if "vgc" in bufs:
+            bufs["vgc"] = tuple(bufs["vgc"][a] for a in range(self.dim))
+        bufs["nan"] = nan.value
+        return bufs
 
     def export_device(self, coeffs, d_out_ptr, what=SB200_X_OMEGA, x_begin=0, x_end=None, d_stats_ptr=None, stream=None):
         c = _f64(coeffs, (self.ncoef,))

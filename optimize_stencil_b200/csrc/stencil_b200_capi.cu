@@ -487,6 +487,57 @@ extern "C" int sb200_export(sb200_ctx* ctx, const double* coeffs, int32_t what, 
     return SB200_OK;
 }
 
+extern "C" int sb200_group_velocity(sb200_ctx* ctx, const double* coeffs, const double* h, double* omega, double* vgc,
+                                    double* vg, double* vph, double* k, int64_t* nan) {
+    if (!ctx) return SB200_EINVAL;
+    if (!coeffs || !h) return fail(ctx, SB200_EINVAL, "coeffs and h must not be NULL");
+    for (int a = 0; a < ctx->dim; ++a)
+        if (ctx->n_user[a] < 3) return fail(ctx, SB200_EINVAL, "numpy.gradient(edge_order=2) needs >= 3 points per axis, axis %d has %d", a, ctx->n_user[a]);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const GridDev& g = ctx->g;
+    const size_t total = (size_t)g.nx * g.ny * g.nz;
+    const int off = ctx->dim == 2 ? 1 : 0;
+    int rc;
+    // device scratch: omega | comps (dim) | vg | vph | k
+    const int nfields = 1 + ctx->dim + 3;
+    if ((rc = grow(ctx, &ctx->d_xbuf, &ctx->d_xbuf_cap, total * nfields))) return rc;
+    double* d_omega = ctx->d_xbuf;
+    if ((rc = export_device_impl(ctx, coeffs, SB200_X_OMEGA, 0, g.nx, d_omega, ctx->d_xstats, ctx->stream))) return rc;
+    GradArgs ga;
+    ga.omega = d_omega;
+    ga.naxes = ctx->dim;
+    for (int a = 0; a < 3; ++a) { ga.comp[a] = nullptr; ga.ax[a] = AxisDiff{1, 1, 0, 0, 0, 0, 0, 0}; }
+    for (int ua = 0; ua < ctx->dim; ++ua) {
+        const int a = ua + off;
+        const double hh = h[ua];
+        AxisDiff d;
+        d.den = 2. * hh; d.rden = 1.0 / d.den;                       // numpy: / (2. * ax_dx)
+        d.a0 = -1.5 / hh; d.b0 = 2. / hh; d.c0 = -0.5 / hh;          // numpy: a, b, c of the near edge
+        d.a1 = 0.5 / hh; d.b1 = -2. / hh; d.c1 = 1.5 / hh;           // ... and of the far edge
+        ga.ax[a] = d;
+        ga.comp[a] = vgc ? d_omega + total * (1 + ua) : nullptr;
+    }
+    ga.vg = vg ? d_omega + total * (1 + ctx->dim) : nullptr;
+    ga.vph = vph ? d_omega + total * (2 + ctx->dim) : nullptr;
+    ga.k = k ? d_omega + total * (3 + ctx->dim) : nullptr;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    gradient_kernel<<<blocks, 256, 0, ctx->stream>>>(g, ga);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SB200_ECUDA, "gradient kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches += 1;
+    const size_t bytes = total * sizeof(double);
+    if (omega) CUDA_TRY(ctx, cudaMemcpyAsync(omega, d_omega, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vgc) CUDA_TRY(ctx, cudaMemcpyAsync(vgc, d_omega + total, bytes * ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vg) CUDA_TRY(ctx, cudaMemcpyAsync(vg, ga.vg, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vph) CUDA_TRY(ctx, cudaMemcpyAsync(vph, ga.vph, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (k) CUDA_TRY(ctx, cudaMemcpyAsync(k, ga.k, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    double st[3];
+    CUDA_TRY(ctx, cudaMemcpyAsync(st, ctx->d_xstats, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nan) *nan = (int64_t)st[2];
+    return SB200_OK;
+}
+
 extern "C" int sb200_get_stream(const sb200_ctx* ctx, void** stream) {
     if (!ctx || !stream) return SB200_EINVAL;
     *stream = (void*)ctx->stream;

@@ -327,27 +327,34 @@ class Dispersion:
         return res
 
     # -- consumers of the dense omega (dispersion.py:199-232, 322-324, 402-413) --------------------
-    def _group_velocity(self, omega):
-        vgs = np.gradient(omega, *self.dks, edge_order=2)
-        vg = np.sqrt(sum(vgc ** 2 for vgc in vgs))
-        vg[(slice(None, 3),) * self.dim] = 1
-        return vgs, vg
+    def _velocity_fields(self, parameters, want):
+        """omega and what the reference derives from it with numpy.gradient (dispersion.py:208-220,
+        408-410), computed on the device in NumPy's own arithmetic.  None when omega() would be None."""
+        self.parameters = parameters
+        e = self._entry(parameters)
+        if e is None or not self._gate(e)[2]:
+            return None
+        f = self._context().group_velocity(e[4], self.dks, want)
+        if f['nan']:
+            raise ValueError('Encountered NaNs in omega for params', parameters)
+        if 'vg' in f:
+            f['vg'][(slice(None, 3),) * self.dim] = 1
+        if 'vph' in f:
+            f['vph'].ravel()[0] = 1.
+        return f
 
     def omega_output(self, fname, parameters):
         """gnuplot-style table: one block per kx index, columns kx ky [kz] k omega vph vg vgx vgy [vgz]."""
-        omega = self.omega(parameters)
-        vgs, vg = self._group_velocity(omega)
-        k = self.k
-        with np.errstate(divide='ignore', invalid='ignore'):
-            vph = omega / k
-        vph.ravel()[0] = 1.
-        cols = np.broadcast_arrays(*self.kappamesh, k, omega, vph, vg, *vgs)
+        f = self._velocity_fields(parameters, ("omega", "vgc", "vg", "vph", "k"))
+        if f is None:
+            raise ValueError('omega is None for params {}: outside the constraints'.format(parameters))
+        cols = np.broadcast_arrays(*self.kappamesh, f['k'], f['omega'], f['vph'], f['vg'], *f['vgc'])
         names = ' '.join('kx ky kz'.split()[:self.dim]) + ' k omega vph vg ' + ' '.join('vgx vgy vgz'.split()[:self.dim])
-        with open(fname, 'wb') as f:
-            f.write(('#' + names + '\n').encode('us-ascii'))
-            for ix in range(omega.shape[0]):
-                np.savetxt(f, np.stack([np.ravel(col[ix]) for col in cols], axis=1))
-                f.write(b'\n')
+        with open(fname, 'wb') as out:
+            out.write(('#' + names + '\n').encode('us-ascii'))
+            for ix in range(cols[0].shape[0]):
+                np.savetxt(out, np.stack([np.ravel(col[ix]) for col in cols], axis=1))
+                out.write(b'\n')
 
     def _corner_min(self, c):
         raise NotImplementedError
@@ -422,7 +429,6 @@ class Dispersion3D(Dispersion):
         return _python_min(b)
 
     def omega_interp(self, parameters):
-        omega = self.omega(parameters)
-        _, vg = self._group_velocity(omega)
+        f = self._velocity_fields(parameters, ("omega", "vg"))
         axes = (self.kx[:, 0, 0], self.ky[0, :, 0], self.kz[0, 0, :])
-        return spinterp.RegularGridInterpolator(axes, omega), spinterp.RegularGridInterpolator(axes, vg)
+        return spinterp.RegularGridInterpolator(axes, f['omega']), spinterp.RegularGridInterpolator(axes, f['vg'])

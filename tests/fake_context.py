@@ -82,6 +82,19 @@ class OracleContext:
         return out, (amin if amin < 0 else 0.0), max(amax, 0.0), int(np.count_nonzero(np.isnan(out)))
 
 
+    def group_velocity(self, coeffs, spacings, want=("omega", "vgc", "vg", "vph", "k")):
+        grid = self.grid
+        c = np.asarray(coeffs, dtype=float)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            A = np.array(np.broadcast_to(O.sqrtarg(grid, c), grid.shape))
+            om = O.omega_from_sqrtarg(A, c[0])
+            vgs = np.gradient(om, *spacings, edge_order=2)
+            f = dict(omega=om, vgc=tuple(vgs), vg=np.sqrt(sum(v ** 2 for v in vgs)), vph=om / grid.k,
+                     k=np.array(np.broadcast_to(grid.k, grid.shape)), nan=int(np.count_nonzero(np.isnan(om))))
+        self.launch_count += 1
+        return {k: v for k, v in f.items() if k in want or k == "nan"}
+
+
 def install(monkeypatch):
     """Route the drop-in package to the oracle-backed context (CPU tests only)."""
     from optimize_stencil_b200 import _capi

@@ -450,3 +450,29 @@ def test_fuzz_against_the_c_oracle(sb):
                 assert np.max(np.where(both_nan, 0.0, relerr(om, want))) <= TOL_OMEGA, (it, fam)
                 n_omega += 1
     assert n_omega >= 20
+
+
+def test_group_velocity_is_numpy_gradient(sb):
+    """sb200_group_velocity against numpy on the SAME omega: gradient components, |vg|, vph and k bitwise
+    (dispersion.py:208-220: np.gradient(omega, *dks, edge_order=2), sqrt of the sum of squares, omega/k)."""
+    for dim, N, Y, Z, fam in ((3, 23, 1.0, 1.0, "StencilFree3D"), (3, 9, 1.4, 0.6, "StencilFree3D"),
+                              (2, 57, 1.0, 1.0, "StencilFree2D"), (2, 3, 2.5, 1.0, "StencilFree2D")):
+        grid = O.Grid(dim, N, Y, Z)
+        p = np.zeros(len(O.parameter_names(fam)))
+        p[0], p[-1] = 0.35, -0.04
+        co = O.coefficients(fam, p)
+        dks = [kc.ravel()[1] for kc in grid.kcomp]
+        with ctx_from_grid(sb, grid) as ctx:
+            f = ctx.group_velocity(co, dks)
+            om = ctx.export(co, 0)[0]
+        np.testing.assert_array_equal(f["omega"], om)
+        vgs = np.gradient(om, *dks, edge_order=2)
+        for a in range(dim):
+            np.testing.assert_array_equal(f["vgc"][a], vgs[a])
+        np.testing.assert_array_equal(f["vg"], np.sqrt(sum(v ** 2 for v in vgs)))
+        np.testing.assert_array_equal(f["k"], np.broadcast_to(grid.k, grid.shape))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            np.testing.assert_array_equal(f["vph"], om / grid.k)
+        assert f["nan"] == 0
+    with ctx_from_grid(sb, O.Grid(2, 2)) as ctx, pytest.raises(sb.StencilB200Error):
+        ctx.group_velocity(O.coefficients("StencilFree2D", [0.3, 0, 0, 0, 0]), [1.0, 1.0])
