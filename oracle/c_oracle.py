@@ -12,7 +12,8 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 class _Grid(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_int), ("n", ctypes.c_int * 3), ("cosk", _dp * 3), ("s2", _dp * 3), ("kcomp", _dp * 3),
-                ("Y", ctypes.c_double), ("Z", ctypes.c_double), ("wkind", ctypes.c_int), ("w", _dp)]
+                ("Y", ctypes.c_double), ("Z", ctypes.c_double), ("Y2", ctypes.c_double), ("Z2", ctypes.c_double),
+                ("wkind", ctypes.c_int), ("w", _dp)]
 
 
 def build(force=False):
@@ -46,6 +47,8 @@ class COracle:
         self._keep = [[np.ascontiguousarray(np.ravel(t[a]), dtype=float) for a in range(dim)] for t in (cos, s2, kcomp)]
         g = _Grid()
         g.dim, g.Y, g.Z = dim, float(Y), float(Z)
+        dx = 1.0
+        g.Y2, g.Z2 = float((Y * dx) ** 2), float((Z * dx) ** 2)   # the reference's expression, with its types
         self.shape = tuple(t.size for t in self._keep[0])
         for a in range(3):
             g.n[a] = self.shape[a] if a < dim else 1

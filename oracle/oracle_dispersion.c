@@ -26,26 +26,28 @@ typedef struct {
     const double* s2[3];
     const double* kcomp[3];
     double Y, Z;
+    double Y2, Z2;       /* (Y*dx)**2, (Z*dx)**2 as the HOST LANGUAGE evaluated them (dispersion.py:319, 398):
+                            Python's / NumPy's x**2 is libm pow, not always the correctly rounded x*x */
     int wkind;           /* 0: w == 1, 1: w[ny*nz] independent of x (dim 3), 2: dense C-order */
     const double* w;
 } oracle_grid;
 
 static inline double sqrtarg3(const double* c, double cx, double cy, double cz, double sx2, double sy2, double sz2,
-                              double Y, double Z) {
+                              double Y2, double Z2) {
     /* c: dt, ax, ay, az, bxy, bxz, byx, byz, bzx, bzy, dlx, dly, dlz   (stencil.py:275) */
     const double dx = 1.0;
     double Ax = c[1] + c[10] * (1.0 + 2.0 * cx) + 2. * c[4] * cy + 2. * c[5] * cz;   /* dispersion.py:394 */
     double Ay = c[2] + c[11] * (1.0 + 2.0 * cy) + 2. * c[6] * cx + 2. * c[7] * cz;   /* :395 */
     double Az = c[3] + c[12] * (1.0 + 2.0 * cz) + 2. * c[8] * cx + 2. * c[9] * cy;   /* :396 */
-    return Ax * sx2 / (dx * dx) + Ay * sy2 / ((Y * dx) * (Y * dx)) + Az * sz2 / ((Z * dx) * (Z * dx)); /* :398 */
+    return Ax * sx2 / (dx * dx) + Ay * sy2 / Y2 + Az * sz2 / Z2;                     /* :398 */
 }
 
-static inline double sqrtarg2(const double* c, double cx, double cy, double sx2, double sy2, double Y) {
+static inline double sqrtarg2(const double* c, double cx, double cy, double sx2, double sy2, double Y2) {
     /* c: dt, ax, ay, bxy, byx, dlx, dly   (stencil.py:209) */
     const double dx = 1.0;
     double Ax = c[1] + c[5] * (1.0 + 2.0 * cx) + 2. * c[3] * cy;                     /* dispersion.py:316 */
     double Ay = c[2] + c[6] * (1.0 + 2.0 * cy) + 2. * c[4] * cx;                     /* :317 */
-    return Ax * sx2 / (dx * dx) + Ay * sy2 / ((Y * dx) * (Y * dx));                  /* :319 */
+    return Ax * sx2 / (dx * dx) + Ay * sy2 / Y2;                                     /* :319 */
 }
 
 static inline void neumaier(double* sum, double* comp, double v) {
@@ -75,11 +77,11 @@ int oracle_objective(const oracle_grid* g, const double* coeffs, int64_t nbatch,
                     double A, k;
                     if (dim == 3) {
                         A = sqrtarg3(c, g->cosk[0][x], g->cosk[1][y], g->cosk[2][z], g->s2[0][x], g->s2[1][y],
-                                     g->s2[2][z], g->Y, g->Z);
+                                     g->s2[2][z], g->Y2, g->Z2);
                         k = sqrt(g->kcomp[0][x] * g->kcomp[0][x] + g->kcomp[1][y] * g->kcomp[1][y] +
                                  g->kcomp[2][z] * g->kcomp[2][z]);                    /* dispersion.py:350 */
                     } else {
-                        A = sqrtarg2(c, g->cosk[0][x], g->cosk[1][y], g->s2[0][x], g->s2[1][y], g->Y);
+                        A = sqrtarg2(c, g->cosk[0][x], g->cosk[1][y], g->s2[0][x], g->s2[1][y], g->Y2);
                         k = sqrt(g->kcomp[0][x] * g->kcomp[0][x] + g->kcomp[1][y] * g->kcomp[1][y]);  /* :276 */
                     }
                     if (A != A) anynan = 1;
@@ -118,8 +120,8 @@ int oracle_export(const oracle_grid* g, const double* c, int what, int x0, int x
         for (int y = 0; y < ny; ++y)
             for (int z = 0; z < nz; ++z) {
                 double A = dim == 3 ? sqrtarg3(c, g->cosk[0][x], g->cosk[1][y], g->cosk[2][z], g->s2[0][x],
-                                               g->s2[1][y], g->s2[2][z], g->Y, g->Z)
-                                    : sqrtarg2(c, g->cosk[0][x], g->cosk[1][y], g->s2[0][x], g->s2[1][y], g->Y);
+                                               g->s2[1][y], g->s2[2][z], g->Y2, g->Z2)
+                                    : sqrtarg2(c, g->cosk[0][x], g->cosk[1][y], g->s2[0][x], g->s2[1][y], g->Y2);
                 double v = A;
                 if (what != 1) {
                     v = sqrt(A);
