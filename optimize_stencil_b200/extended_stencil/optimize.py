@@ -25,12 +25,33 @@ import sys
 import numpy as np
 import scipy.optimize as scop
 
-from .dispersion import Dispersion2D, Dispersion3D
+from .dispersion import Dispersion2D, Dispersion3D, FD_STEP
 from .stencil import get_stencil
 from .weight import weight_functions
 
 
-class make_single_max_constraint:
+class _single_constraint:
+    """Box constraint on one parameter.  `jac` is SciPy's own forward difference of it
+    (approx_derivative, '2-point', abs_step=FD_STEP: (f(x + h e_i) - f(x)) / ((x_i + h) - x_i)), evaluated
+    in closed form; it is what SLSQP would compute itself, minus the Python overhead."""
+
+    def jac(self, p):
+        p = np.asarray(p, dtype=float)
+        i = self.index
+        xi = p[i]
+        dx = (xi + FD_STEP) - xi
+        f0 = self(p)
+        if dx == 0 or not np.isfinite(f0):
+            from scipy.optimize._numdiff import approx_derivative
+            return approx_derivative(self, p, method='2-point', abs_step=FD_STEP)
+        J = np.zeros(len(p))
+        x1 = p.copy()
+        x1[i] = xi + FD_STEP
+        J[i] = (self(x1) - f0) / dx
+        return J
+
+
+class make_single_max_constraint(_single_constraint):
     """p[index] <= maxval as an SLSQP 'ineq' function."""
 
     def __init__(self, index, maxval):
@@ -40,7 +61,7 @@ class make_single_max_constraint:
         return self.maxval - p[self.index]
 
 
-class make_single_min_constraint:
+class make_single_min_constraint(_single_constraint):
     """p[index] >= minval as an SLSQP 'ineq' function."""
 
     def __init__(self, index, minval):
@@ -55,6 +76,10 @@ SLSQP_OPTIONS = dict(disp=False, iprint=2)
 
 class Optimize:
     """Holds the low- and high-resolution dispersion objects and runs the start-grid scan."""
+
+    # Hand SciPy the finite differences it would take anyway (same points, same arithmetic, from the
+    # result cache).  The search is bit-identical either way; OPTSTENCIL_FD_JAC=0 lets SciPy do them.
+    exact_fd_jac = os.environ.get('OPTSTENCIL_FD_JAC', '1') != '0'
 
     def __init__(self, args):
         self.args = args
@@ -86,7 +111,18 @@ class Optimize:
             lo, hi = getattr(self.args, fname + 'range')
             cons.append(dict(type='ineq', fun=make_single_min_constraint(i, lo)))
             cons.append(dict(type='ineq', fun=make_single_max_constraint(i, hi)))
+        if self.exact_fd_jac:
+            cons[0]['jac'], cons[1]['jac'] = dispersion.stencil_ok_fd, dispersion.dt_ok_fd
+            for con in cons[2:]:
+                con['jac'] = con['fun'].jac
         return cons
+
+    def _minimize(self, dispersion, constraints, x0):
+        """scipy.optimize.minimize exactly as the reference calls it (optimize.py:136, 142).  With
+        `exact_fd_jac` the forward differences SLSQP would take itself are supplied as `jac`."""
+        jac = dispersion.norm_fd if self.exact_fd_jac else None
+        return scop.minimize(dispersion.norm, x0, method='SLSQP', jac=jac, constraints=constraints,
+                             options=dict(SLSQP_OPTIONS))
 
     # -- one start (optimize.py:115-139) ----------------------------------------------------------
     def _optimize_single(self, x0):
@@ -100,13 +136,11 @@ class Optimize:
         x0 = np.asarray(x0, dtype=float)
         if self.dispersion.stencil_ok(x0) < 0:
             return x0, None, float('inf')
-        res = scop.minimize(self.dispersion.norm, x0, method='SLSQP', constraints=self.constraints,
-                            options=dict(SLSQP_OPTIONS))
+        res = self._minimize(self.dispersion, self.constraints, x0)
         return x0, res, self.dispersion_high.norm(res.x)
 
     def _optimize_final(self, x0):
-        res = scop.minimize(self.dispersion_high.norm, x0, method='SLSQP', constraints=self.constraints_high,
-                            options=dict(SLSQP_OPTIONS))
+        res = self._minimize(self.dispersion_high, self.constraints_high, x0)
         print('x0={}, x={}, norm={}'.format(x0, res.x, res.fun))
         return res, res.fun
 

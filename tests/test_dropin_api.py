@@ -257,6 +257,39 @@ def test_optimize_default_config1(es):
     assert np.asarray(opt.dispersion_high.stencil_ok(x)).ravel()[0] > 0
 
 
+@pytest.mark.parametrize("name", ["divfree", "divfree3d_small"])
+def test_exact_fd_jacobians_leave_the_search_unchanged(es, name, capsys, monkeypatch):
+    """The `jac` callables handed to SLSQP reproduce scipy's approx_derivative('2-point', abs_step=eps)
+    bit for bit, so every printed line and the result are identical with and without them."""
+    runs = {}
+    for flag in (False, True):
+        monkeypatch.setattr(es.Optimize, "exact_fd_jac", flag)
+        opt = es.Optimize(default_args(**OPT_RUNS[name]))
+        assert ("jac" in opt.constraints[0]) == flag
+        x, fmin = opt.optimize()
+        runs[flag] = (x, fmin, capsys.readouterr().out, opt.dispersion.stats["launches"])
+    assert np.array_equal(runs[False][0], runs[True][0]) and runs[False][1] == runs[True][1]
+    assert runs[False][2] == runs[True][2]
+    assert runs[False][3] == runs[True][3]
+
+
+def test_fd_jacobians_equal_scipy_approx_derivative(es):
+    from scipy.optimize._numdiff import approx_derivative
+    from optimize_stencil_b200.extended_stencil.dispersion import FD_STEP
+    rng = np.random.default_rng(5)
+    d = es.Dispersion2D(1.25, 24, es.StencilFree2D())
+    pts = [np.array([0.5, 0.05, -0.02, -0.1, -0.12]), np.array([0.9, 0.3, 0.2, 0.1, 0.1]),   # usable / gated
+           np.array([0.5, -0.0, 0.0, -0.1, 1e9])]                                               # -0.0 and dx == 0
+    pts += [np.array([0.6, 0, 0, -0.1, -0.1]) + 0.05 * rng.standard_normal(5) for _ in range(6)]
+    with np.errstate(all="ignore"):
+        for p in pts:
+            for fun, jac in ((d.norm, d.norm_fd), (d.stencil_ok, d.stencil_ok_fd), (d.dt_ok, d.dt_ok_fd)):
+                want = approx_derivative(fun, p, method="2-point", abs_step=FD_STEP)
+                np.testing.assert_array_equal(jac(p), want)
+            for con in (es.make_single_max_constraint(2, 0.25), es.make_single_min_constraint(4, -1.0)):
+                np.testing.assert_array_equal(con.jac(p), approx_derivative(con, p, method="2-point", abs_step=FD_STEP))
+
+
 def test_start_grid(es):
     opt = es.Optimize(default_args(N=2, scan_dt=False))
     starts = opt.start_grid()
