@@ -5,6 +5,18 @@
 // device is usable every compute entry point returns SB200_ECUDA and says why.
 #include "../../include/stencil_b200.h"
 #include "dispersion_kernels.cuh"
+#include "objective_fa.cuh"
+
+// 1: regrouped sqrtarg in the hot loop, reference order only where bit-identity matters (objective_fa.cuh);
+// 0: reference order at every k-point (objective_kernel).  Same results contract either way.
+#ifndef SB200_FAST_A
+#define SB200_FAST_A 1
+#endif
+#if SB200_FAST_A
+#define SB200_OBJECTIVE_KERNEL objective_kernel_fa
+#else
+#define SB200_OBJECTIVE_KERNEL objective_kernel
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -251,10 +263,16 @@ struct Plan {
 };
 
 size_t smem_bytes(int C, int TY, int TZ) {
-    const int row = ((2 + 3 * C) + 1) & ~1;  // RowLayout<C>::ROW
     const int nwarps = (TZ + 31) / 32;
     (void)TY;                                // tables are per warp (32 rows), not per y tile
+#if SB200_FAST_A
+    const int row = 2 + 2 * C;               // RowLayoutFA<C>::ROW
+    return (size_t)C * sizeof(Cand) + (size_t)((C + 1) & ~1) * 8 + (size_t)nwarps * 32 * row * 8 +
+           (size_t)C * 8 * 8 * 4 + (size_t)C * TZ * 8 * 2;
+#else
+    const int row = ((2 + 3 * C) + 1) & ~1;  // RowLayout<C>::ROW
     return (size_t)C * sizeof(Cand) + (size_t)nwarps * 32 * row * 8 + (size_t)C * 8 * 8 * 4 + (size_t)C * TZ * 8;
+#endif
 }
 
 Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
@@ -297,7 +315,7 @@ cudaError_t launch_objective(const sb200_ctx* ctx, const Plan& p, const BatchArg
     dim3 grid((unsigned)(p.n_chunks * p.n_ztiles), (unsigned)p.n_xchunks, (unsigned)p.n_ychunks), block(p.TZ);
 #define SB200_LAUNCH(UNIT, WK)                                                                              \
     do {                                                                                                    \
-        auto kern = objective_kernel<C, UNIT, WK>;                                                          \
+        auto kern = SB200_OBJECTIVE_KERNEL<C, UNIT, WK>;                                                    \
         if (p.smem > 48 * 1024) {                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
             if (e != cudaSuccess) return e;                                                                 \
