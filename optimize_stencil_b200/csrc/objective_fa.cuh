@@ -15,25 +15,26 @@
 //
 // A' (regrouped) and A (reference order) both approximate the real-number value with an error below
 // 8u * M, M = sum of the magnitudes of all products <= Mbound(candidate); |A' - A| <= 2^-49 Mbound.
-// A lane asks for the exact value when the high word of A' is
-//     >= thr   = min(high word of the thread's running exact maximum - 1, high word of the CFL threshold)
-//  or <  LO    = high word of 2^-40        (also true for every negative or NaN A': sign bit / all-ones)
-// in ONE unsigned compare of (hi(A') - LO) against (thr - LO).  If any lane of the warp asks, the whole
-// iteration is redone from the tables in the reference's order (sqrtarg_exact_at) and only those exact
-// values feed the extrema.  With rows walked from high x, y to low this happens about once per plane.
+// All four tables carry the factor 2 dt^2, so the three instructions give W' = 2 dt^2 A' and v = W' - 1.
+// A lane asks for the exact value
+//   (1) when the high word of W' reaches thr = high word of (2 dt^2 * the thread's running exact maximum) - 2
+//       -- ONE signed integer compare per evaluation, the only extra work in the common (MID) path;
+//   (2,3) outside the MID class only: v <= -1 + 2^-21, v >= 1 - 2^-9 - 2^-12 or NaN.
+// If any lane of the warp asks, the whole iteration is redone from the tables in the reference's order
+// (sqrtarg_exact_at) and only those exact values feed the extrema.  With rows walked from high x, y to low
+// this happens about once per plane.
 //
-// The guards are sufficient when  Mbound <= 64  (2^-46 Mbound <= 2^-40),
-//                                 Mbound <= 2^23 * A(last visited corner)  (one high-word unit of margin
-//                                        at the maximum exceeds 2 * 2^-46 Mbound),
-//                                 dt^2 Mbound <= 2^30  (the CFL threshold's 2^-12 slack exceeds the error of v).
-// A candidate that fails any of them (huge or cancelling coefficients, NaNs, negative corner) makes its
+// The guards are sufficient when  Mbound <= 2^23 * A(last visited corner)   (two high-word units at the
+//                                        maximum, >= 2^-21 relative, exceed twice the error 2^-49 Mbound)
+//                                 2 dt^2 Mbound <= 2^27   (the error of W' stays below 2^-22: a negative
+//                                        sqrtarg gives W' <= 2^-22, and the CFL test keeps 2^-13 of slack).
+// A candidate that fails either (huge or cancelling coefficients, NaNs, negative corner) makes its
 // CTA take the exact path at every point: same results as objective_kernel, at about half the speed.
 #pragma once
 #include "dispersion_kernels.cuh"
+#include <climits>
 
 namespace sb200 {
-
-#define SB200_FA_LO 0x3D700000u   // high word of 2^-40
 
 // sqrtarg at one k-point from the per-axis tables, reference order (dispersion.py:394-398).  Rare path.
 template <bool UNIT>
@@ -64,7 +65,7 @@ struct RowLayoutFA {
     static constexpr int ROWS = 32;
 };
 
-// Shared memory: Cand[C] | guards[C] (uint2: cfl_hi, force) | rows | s_red | s_redu | s_umax | s_smax
+// Shared memory: Cand[C] | rows | s_red | s_redu | s_umax | s_smax
 template <int C, bool UNIT, int WK>
 __global__ void __launch_bounds__(SB200_MAXTHREADS, (C <= 4 ? SB200_MINBLOCKS_C4 : SB200_MINBLOCKS_C8))
 objective_kernel_fa(const GridDev g, const BatchArgs a) {
@@ -72,16 +73,15 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     constexpr int ROWS = RowLayoutFA<C>::ROWS;
     constexpr int U = (C >= 4) ? 1 : 4 / C;   // rows per iteration
     constexpr int J = U * C;                  // independent chains per iteration
+    constexpr unsigned int FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Cand* cand = reinterpret_cast<Cand*>(smem_raw);
-    uint2* guard = reinterpret_cast<uint2*>(cand + C);                                   // [C] (+ pad to 16 B)
-    double* s_rows = reinterpret_cast<double*>(guard + ((C + 1) & ~1));                  // [nwarps][ROWS][ROW]
+    double* s_rows = reinterpret_cast<double*>(cand + C);                                // [nwarps][ROWS][ROW]
     const int nwarps = (blockDim.x + 31) >> 5;
     double* s_red = s_rows + (size_t)nwarps * ROWS * ROW;                                // [C][8]
     unsigned long long* s_redu = reinterpret_cast<unsigned long long*>(s_red + C * 8);   // [3][C][8]
     unsigned long long* s_umax = s_redu + 3 * C * 8;   // [C][blockDim.x] most negative exact value (raw bits)
     long long* s_smax = reinterpret_cast<long long*>(s_umax + (size_t)C * blockDim.x);   // [C][blockDim.x] max(exact, +0)
-    __shared__ unsigned int s_ticket;
     __shared__ int s_force;
 
     const int tid = threadIdx.x;
@@ -109,24 +109,19 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const int xc = a.x_end - 1, yc = g.ny - 1, zc = g.nz - 1;
         const double corner = sqrtarg_exact_at<UNIT>(&c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc],
                                                      g.sz2[zc], g.Y2, g.rY2, g.Z2, g.rZ2);
-        const bool sane = (mb <= 64.) && (mb <= 8388608. * corner) && (c.dt2 * mb <= 1073741824.);
-        // sqrtarg from which v = 2 dt^2 A - 1 may reach 1 - 2^-9 (the EXACT class), with 2^-12 of slack
-        const double acfl = (2. - 0x1p-9 - 0x1p-12) / c.c2dt.x;
-        unsigned int cfl_hi = 0x7ff00000u;
-        if (acfl >= 0. && acfl < __longlong_as_double(0x7ff0000000000000ll)) cfl_hi = (unsigned int)__double2hiint(acfl);
-        guard[tid] = make_uint2(cfl_hi, sane ? 0u : 1u);
+        const bool sane = (mb <= 8388608. * corner) && (c.c2dt.x * mb <= 134217728.);
         if (!sane) atomicOr(&s_force, 1);
     }
     __syncthreads();
     const bool force = s_force != 0;   // CTA-uniform
 
-    // Per-thread state.  T and tzy hold the z-dependent parts for the thread's current z; span is the
-    // filter threshold minus LO (0 = "always ask", the initial state).
-    double T[C], tzy[C], S[C];
-    unsigned int span[C];
+    // Per-thread state.  Ts and tzys hold the z-dependent parts for the thread's current z (scaled by
+    // 2 dt^2); thr is the high-word threshold of the maximum filter (INT_MIN = "always ask").
+    double Ts[C], tzys[C], dtc[C], S[C];
+    int thr[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        S[c] = 0.; span[c] = 0u;
+        S[c] = 0.; thr[c] = INT_MIN; dtc[c] = cand[c].dt;
         s_umax[c * blockDim.x + tid] = 0ull;   // own slots only: no barrier needed
         s_smax[c * blockDim.x + tid] = 0ll;
     }
@@ -137,31 +132,31 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         // therefore takes z slice (w + x) mod nwarps of the CTA's z tile for plane x, so that over an
         // x range every warp sees every z slice and all warps of the CTA finish together.
         const int zslice = (warp + (x - a.x_begin)) % nwarps;
-        const int z = ztile * blockDim.x + zslice * 32 + lane;
-        const bool active = z < g.nz;
-        const unsigned int amask = __ballot_sync(0xffffffffu, active);   // lanes that own a z index
-        if (amask == 0u) continue;                                        // warp-uniform
+        const int zraw = ztile * blockDim.x + zslice * 32 + lane;
+        // Lanes past the end of the z axis repeat its last point: all 32 lanes stay converged (votes with
+        // a constant full mask), the extrema are unaffected and their sums are simply not accumulated.
+        const bool active = zraw < g.nz;
+        if (__ballot_sync(FULL, active) == 0u) continue;                  // warp-uniform
+        const int z = min(zraw, g.nz - 1);
         const double cx = g.cx[x], sx2 = g.sx2[x], kx2 = g.kx2[x];
         const double opx = __dadd_rn(1.0, __dmul_rn(2.0, cx));
-        double sz2r = 0., kz2 = 0.;
-        if (active) {
-            const double cz = g.cz[z];
-            sz2r = __dmul_rn(g.sz2[z], rZ);
-            kz2 = g.kz2[z];
-            const double opz = __dadd_rn(1.0, __dmul_rn(2.0, cz));
+        const double cz = g.cz[z];
+        const double sz2r = __dmul_rn(g.sz2[z], rZ);
+        const double kz2 = g.kz2[z];
+        const double opz = __dadd_rn(1.0, __dmul_rn(2.0, cz));
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const double tzx = __dmul_rn(cand[c].bxz2, cz);
-                const double tzzx = fma(cand[c].bzx2, cx, fma(cand[c].dlz, opz, cand[c].az));
-                tzy[c] = __dmul_rn(cand[c].byz2, cz);
-                T[c] = fma(tzx, sx2, __dmul_rn(tzzx, sz2r));
-            }
+        for (int c = 0; c < C; ++c) {
+            const double c2 = cand[c].c2dt.x;
+            const double tzx = __dmul_rn(cand[c].bxz2, cz);
+            const double tzzx = fma(cand[c].bzx2, cx, fma(cand[c].dlz, opz, cand[c].az));
+            tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
+            Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
         }
         for (int y1 = ye; y1 > ys; y1 -= ROWS) {          // y tiles from the top of the range downwards
             const int y0 = max(ys, y1 - ROWS);
             const int nrows = y1 - y0;
             __syncwarp();                      // every lane is done reading the previous tile
-            {                                  // lane l builds row l (all 32 lanes, active or not);
+            {                                  // lane l builds row l
                 const int y = min(y0 + lane, y1 - 1);   // rows past the tile's end repeat its last row
                 const double cy = g.cy[y];
                 const double opy = __dadd_rn(1.0, __dmul_rn(2.0, cy));
@@ -170,16 +165,16 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                 *reinterpret_cast<double2*>(row) = make_double2(sy2r, __dadd_rn(kx2, g.ky2[y]));
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
+                    const double c2 = cand[c].c2dt.x;
                     const double axy = fma(cand[c].bxy2, cy, fma(cand[c].dlx, opx, cand[c].ax));
                     const double ayx = fma(cand[c].byx2, cx, fma(cand[c].dly, opy, cand[c].ay));
                     double2 v;
-                    v.x = fma(axy, sx2, __dmul_rn(ayx, sy2r));
-                    v.y = __dmul_rn(cand[c].bzy2, cy);
+                    v.x = __dmul_rn(c2, fma(axy, sx2, __dmul_rn(ayx, sy2r)));
+                    v.y = __dmul_rn(c2, __dmul_rn(cand[c].bzy2, cy));
                     *reinterpret_cast<double2*>(row + 2 + 2 * c) = v;
                 }
             }
             __syncwarp();
-            if (!active) continue;
             const double* wrow = nullptr;
             if (WK == 1) wrow = g.w + (size_t)y0 * g.nz + z;
             if (WK == 2) wrow = g.w + ((size_t)x * g.ny + y0) * g.nz + z;
@@ -189,8 +184,9 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
             const double* row = wrows + (size_t)(nit - 1) * U * ROW;
 #pragma unroll 1
             for (int yy = (nit - 1) * U; yy >= 0; yy -= U, row -= U * ROW) {
-                double A[J], v[J], e[J], hk[J], w[U];
-                bool need = force, all_mid = true;
+                // W = 2 dt^2 A (regrouped), v = W - 1 = 2 s^2 - 1, t = v^2, hk = pi/2 - k dt
+                double W[J], A[J], v[J], t[J], e[J], hk[J], w[U];
+                bool need = false, all_mid = true;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double* r = row + u * ROW;
@@ -201,23 +197,25 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int j = u * C + c;
-                        const double2 t = *reinterpret_cast<const double2*>(r + 2 + 2 * c);   // (R, bzy)
-                        A[j] = fma(tzy[c], yk.x, fma(t.y, sz2r, __dadd_rn(t.x, T[c])));
-                        need = need || ((unsigned int)__double2hiint(A[j]) - SB200_FA_LO >= span[c]);
-                        const double2 cd = cand[c].c2dt;                        // (2 dt^2, dt), warp-broadcast
-                        v[j] = fma(cd.x, A[j], -1.0);                           // 2 s^2 - 1
-                        hk[j] = fma(-k, cd.y, SB200_PI_2);                      // pi/2 - k dt
-                        all_mid = all_mid && v_is_mid(v[j]);
+                        const double2 q = *reinterpret_cast<const double2*>(r + 2 + 2 * c);   // 2dt^2 * (R, bzy)
+                        W[j] = fma(tzys[c], yk.x, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c])));
+                        need = need || (__double2hiint(W[j]) >= thr[c]);
+                        v[j] = __dadd_rn(W[j], -1.0);
+                        hk[j] = fma(-k, dtc[c], SB200_PI_2);
+                        t[j] = __dmul_rn(v[j], v[j]);
+                        all_mid = all_mid && ((unsigned int)__double2hiint(t[j]) <= 0x3fd00000u);   // |v| <= 1/2, not NaN
                     }
                 }
-                if (__any_sync(amask, need)) {
-                    // Rare: redo the iteration in the reference's operation order and let the exact values
-                    // (and only those) into the extrema.
-                    const double czr = ld_rare(g.cz + z), sz2 = ld_rare(g.sz2 + z);
+                // Rare: redo the iteration in the reference's operation order and let the exact values (and
+                // only those) into the extrema.  The opaque copies keep the address arithmetic in here.
+                auto redo_exact = [&]() {
+                    int zq = z, yq = yy;
+                    asm volatile("" : "+r"(zq), "+r"(yq));
+                    const double czr = ld_rare(g.cz + zq), sz2 = ld_rare(g.sz2 + zq);
                     all_mid = true;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int y = y0 + min(yy + u, nrows - 1);
+                        const int y = y0 + min(yq + u, nrows - 1);
                         const double cyr = ld_rare(g.cy + y), sy2 = ld_rare(g.sy2 + y);
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
@@ -231,22 +229,50 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                                 unsigned long long* um = s_umax + c * blockDim.x + tid;
                                 *um = max(*um, (unsigned long long)bits);
                             }
+                            const double c2 = cand[c].c2dt.x;
                             A[j] = Ae;
-                            v[j] = fma(cand[c].c2dt.x, Ae, -1.0);
-                            all_mid = all_mid && v_is_mid(v[j]);
+                            W[j] = __dmul_rn(c2, Ae);
+                            v[j] = fma(c2, Ae, -1.0);
+                            t[j] = __dmul_rn(v[j], v[j]);
+                            all_mid = all_mid && ((unsigned int)__double2hiint(t[j]) <= 0x3fd00000u);
                         }
                     }
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const unsigned int hm = (unsigned int)(s_smax[c * blockDim.x + tid] >> 32);
-                        const unsigned int thr = min(max(hm, 1u) - 1u, guard[c].x);
-                        span[c] = max(thr, SB200_FA_LO) - SB200_FA_LO;
+                        const double wm = __dmul_rn(cand[c].c2dt.x, __longlong_as_double(s_smax[c * blockDim.x + tid]));
+                        thr[c] = force ? INT_MIN : max(__double2hiint(wm), 2) - 2;
                     }
+                };
+                const bool redone = __any_sync(FULL, need);
+                if (redone) redo_exact();
+                if (__all_sync(FULL, all_mid)) {
+                    // |v| <= 1/2 for every lane and chain: dt*omega = pi/2 + v f(v^2), no square root
+#pragma unroll
+                    for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
+                } else {
+                    if (!redone) {
+                        // v <= -1 + 2^-21 (sqrtarg may be negative), v >= 1 - 2^-9 - 2^-12 (EXACT class), NaN
+                        need = false;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const int hv = __double2hiint(v[j]);
+                            need = need || ((unsigned int)hv >= 0xbfefffffu) || (hv >= 0x3fefee00);
+                        }
+                        if (__any_sync(FULL, need)) {
+                            redo_exact();
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < J; ++j) A[j] = W[j];   // never read: no lane is in the EXACT class
+                        }
+                    }
+                    double z2[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);
+                    scaled_dev_nonmid<C, J>(A, z2, v, hk, e, cand, FULL);
                 }
-                scaled_dev_chains<C, J>(A, v, hk, e, cand, amask, all_mid);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (U == 1 || yy + u < nrows) {       // rows past the end are repeats: skip their sum only
+                    if (active && (U == 1 || yy + u < nrows)) {   // rows past the end are repeats: skip their sum only
 #pragma unroll
                         for (int c = 0; c < C; ++c) {     // dispersion.py:251, times dt^2
                             const int j = u * C + c;
@@ -258,81 +284,14 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         }
     }
 
-    // ---- CTA reduction: fixed shuffle tree, then warp leaders in order -------------------------
+    unsigned long long um[C];
+    long long sm[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        double s = S[c];
-        unsigned long long um = s_umax[c * blockDim.x + tid];
-        long long sm = s_smax[c * blockDim.x + tid];
-        // A NaN omega makes the thread's sum NaN (w*(NaN-k)^2 accumulates by fma); the per-candidate
-        // NaN indicator is therefore taken from the partial sums instead of being counted per point.
-        unsigned long long nn = (s != s) ? 1ull : 0ull;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-            um = max(um, __shfl_down_sync(0xffffffffu, um, off));
-            sm = max(sm, __shfl_down_sync(0xffffffffu, sm, off));
-            nn += __shfl_down_sync(0xffffffffu, nn, off);
-        }
-        if (lane == 0) {
-            s_red[c * 8 + warp] = s;
-            s_redu[(0 * C + c) * 8 + warp] = um;
-            s_redu[(1 * C + c) * 8 + warp] = (unsigned long long)sm;
-            s_redu[(2 * C + c) * 8 + warp] = nn;
-        }
+        um[c] = s_umax[c * blockDim.x + tid];
+        sm[c] = s_smax[c * blockDim.x + tid];
     }
-    __syncthreads();
-    const int slot = (ztile * a.n_xchunks + blockIdx.y) * a.n_ychunks + blockIdx.z;
-    if (tid < C) {
-        double s = s_red[tid * 8];
-        unsigned long long um = s_redu[(0 * C + tid) * 8], nn = s_redu[(2 * C + tid) * 8];
-        long long sm = (long long)s_redu[(1 * C + tid) * 8];
-        for (int wq = 1; wq < nwarps; ++wq) {
-            s = __dadd_rn(s, s_red[tid * 8 + wq]);
-            um = max(um, s_redu[(0 * C + tid) * 8 + wq]);
-            sm = max(sm, (long long)s_redu[(1 * C + tid) * 8 + wq]);
-            nn += s_redu[(2 * C + tid) * 8 + wq];
-        }
-        const size_t o = (size_t)(b0 + tid) * a.P + slot;
-        a.part_S[o] = s; a.part_min[o] = um; a.part_max[o] = (unsigned long long)sm; a.part_nan[o] = nn;
-        __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&a.tickets[chunk], 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned int)(a.P - 1)) return;
-
-    // ---- last CTA of this candidate chunk: fixed-order reduction over the P slots ---------------
-    __threadfence();
-    for (int c = warp; c < C; c += nwarps) {
-        const long long b = b0 + c;
-        if (b >= a.B) continue;
-        const size_t o = (size_t)b * a.P;
-        double s = 0.;
-        Extrema e;
-        ext_init(e);
-        unsigned long long nn = 0ull;
-        for (int p = lane; p < a.P; p += 32) {
-            s = __dadd_rn(s, __ldcg(a.part_S + o + p));
-            ext_merge(e, __ldcg(a.part_min + o + p), (long long)__ldcg(a.part_max + o + p));
-            nn += __ldcg(a.part_nan + o + p);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-            ext_merge(e, __shfl_down_sync(0xffffffffu, e.umax, off), __shfl_down_sync(0xffffffffu, e.smax, off));
-            nn += __shfl_down_sync(0xffffffffu, nn, off);
-        }
-        if (lane == 0) {
-            double amin, amax;
-            ext_final(e, amin, amax);
-            a.out[0 * a.B + b] = __ddiv_rn(s, cand[c].dt2);   // the sum was taken over (dt*(omega-k))^2
-            a.out[1 * a.B + b] = amin;
-            a.out[2 * a.B + b] = amax;
-            a.out[3 * a.B + b] = (double)nn;
-        }
-    }
-    if (tid == 0) a.tickets[chunk] = 0u;  // re-arm for the next launch
+    finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk, ztile, b0);
 }
 
 }  // namespace sb200

@@ -267,7 +267,7 @@ size_t smem_bytes(int C, int TY, int TZ) {
     (void)TY;                                // tables are per warp (32 rows), not per y tile
 #if SB200_FAST_A
     const int row = 2 + 2 * C;               // RowLayoutFA<C>::ROW
-    return (size_t)C * sizeof(Cand) + (size_t)((C + 1) & ~1) * 8 + (size_t)nwarps * 32 * row * 8 +
+    return (size_t)C * sizeof(Cand) + (size_t)nwarps * 32 * row * 8 +
            (size_t)C * 8 * 8 * 4 + (size_t)C * TZ * 8 * 2;
 #else
     const int row = ((2 + 3 * C) + 1) & ~1;  // RowLayout<C>::ROW

@@ -143,7 +143,9 @@ def test_batch_api_matches_scalar_api(es):
     assert launches == 1
     ref = es.Dispersion3D(1.2, 0.9, 14, es.StencilFree3D())
     for i in range(12):
-        assert out["norm"][i] == ref.norm(P[i])
+        # the constraints come from the bit-exact extrema; the sum may differ in its last bits between two
+        # launches of different batch composition (the contract is determinism per launch shape, and 1e-12)
+        assert relerr(out["norm"][i], ref.norm(P[i])) <= 1e-13
         assert out["stencil_ok"][i] == np.asarray(ref.stencil_ok(P[i]), dtype=float).ravel()[0]
         assert out["dt_ok"][i] == np.asarray(ref.dt_ok(P[i]), dtype=float).ravel()[0]
     np.testing.assert_array_equal(d.norm_batch(P), out["norm"])
