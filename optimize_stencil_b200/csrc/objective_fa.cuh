@@ -193,7 +193,9 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                     const double2 yk = *reinterpret_cast<const double2*>(r);   // (sy2r, kx2+ky2)
                     w[u] = 1.0;
                     if (WK != 0) w[u] = __ldg(wrow + (size_t)min(yy + u, nrows - 1) * g.nz);
-                    const double k = sqrt_fast(__dadd_rn(yk.y, kz2));           // dispersion.py:350
+                    // |k| (dispersion.py:350) to 1 ulp: its rounding enters (omega - k) like omega's own
+                    // (2.8e-15) and far below it; the correctly rounded version costs 4 more instructions per row
+                    const double k = sqrt_approx(__dadd_rn(yk.y, kz2));
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int j = u * C + c;
@@ -201,7 +203,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                         W[j] = fma(tzys[c], yk.x, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c])));
                         need = need || (__double2hiint(W[j]) >= thr[c]);
                         v[j] = __dadd_rn(W[j], -1.0);
-                        hk[j] = fma(-k, dtc[c], SB200_PI_2);
+                        hk[j] = fma(-k, dtc[c], kPi2);
                         t[j] = __dmul_rn(v[j], v[j]);
                         all_mid = all_mid && ((unsigned int)__double2hiint(t[j]) <= 0x3fd00000u);   // |v| <= 1/2, not NaN
                     }

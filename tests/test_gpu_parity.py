@@ -310,7 +310,10 @@ def test_nan_and_inf_coefficients_do_not_poison_neighbours(sb):
     co = np.stack([good, bad1, good, bad2, good])
     with ctx_from_grid(sb, grid) as ctx:
         S, Amin, Amax, nan = ctx.objective_batch(co)
-        assert S[0] == S[2] == S[4] and np.isfinite(S[0]) and nan[0] == 0
+        # rows 0 and 2 share a candidate chunk with the NaN row (whose CTA evaluates sqrtarg in the reference
+        # order everywhere), row 4 does not: same value up to the rounding of the sum, same extrema bit for bit
+        assert S[0] == S[2] and relerr(S[4], S[0]) <= 1e-13 and np.isfinite(S[0]) and nan[0] == 0
+        assert same_bits(Amax[0], Amax[4]) and same_bits(Amin[0], Amin[4]) and same_bits(Amax[0], Amax[2])
         assert np.isnan(S[1]) and np.isnan(Amin[1]) and np.isnan(Amax[1]) and nan[1] > 0
         assert np.isnan(S[3]) and nan[3] > 0
         assert relerr(S[0], O.device_contract(grid, good)[0]) <= TOL_S
