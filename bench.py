@@ -311,7 +311,7 @@ def run_gpu_arm(a):
         except Exception:
             traffic = None
     roofline = dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                    traffic=traffic, kernel="sb200::objective_kernel<4,true,0>",
+                    traffic=traffic, kernel="sb200::objective_kernel_fa<4,true,0>",
                     flop_per_eval=F_ALG_3D, evals_per_launch=launch_evals, launch_ms=launch_ms,
                     peak_source="DFMA microbenchmark (sb200_fp64_peak) measured in this run on this GPU; "
                                 "MEASURED_PEAKS.json has no FP64 entry",

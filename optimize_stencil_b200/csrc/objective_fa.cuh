@@ -24,12 +24,15 @@
 // (sqrtarg_exact_at) and only those exact values feed the extrema.  With rows walked from high x, y to low
 // this happens about once per plane.
 //
-// The guards are sufficient when  Mbound <= 2^23 * A(last visited corner)   (two high-word units at the
+// The guards are sufficient when  Mbound <= 2^23 * Amax                     (two high-word units at the
 //                                        maximum, >= 2^-21 relative, exceed twice the error 2^-49 Mbound)
 //                                 2 dt^2 Mbound <= 2^27   (the error of W' stays below 2^-22: a negative
 //                                        sqrtarg gives W' <= 2^-22, and the CFL test keeps 2^-13 of slack).
-// A candidate that fails either (huge or cancelling coefficients, NaNs, negative corner) makes its
-// CTA take the exact path at every point: same results as objective_kernel, at about half the speed.
+// The kernel asks for much more, Mbound <= 16 * P with P = the largest sqrtarg on the 8 corners of the
+// visited slab (a lower bound of Amax): that also keeps the relative error of A' (and so of omega, 1e-13
+// being the bar) at a few 1e-15 -- real stencils have Mbound / P of 1 to 3.
+// A candidate that fails (huge or cancelling coefficients, NaNs, non-positive corners) makes its
+// CTA take the exact path at every point: same results as objective_kernel, at about a quarter of the speed.
 #pragma once
 #include "dispersion_kernels.cuh"
 #include <climits>
@@ -106,10 +109,15 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const double mb = (fabs(c.ax) + 3. * fabs(c.dlx) + fabs(c.bxy2) + fabs(c.bxz2)) +
                           (fabs(c.ay) + 3. * fabs(c.dly) + fabs(c.byx2) + fabs(c.byz2)) * rY +
                           (fabs(c.az) + 3. * fabs(c.dlz) + fabs(c.bzx2) + fabs(c.bzy2)) * rZ;
-        const int xc = a.x_end - 1, yc = g.ny - 1, zc = g.nz - 1;
-        const double corner = sqrtarg_exact_at<UNIT>(&c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc],
-                                                     g.sz2[zc], g.Y2, g.rY2, g.Z2, g.rZ2);
-        const bool sane = (mb <= 8388608. * corner) && (c.c2dt.x * mb <= 134217728.);
+        // a lower bound of the grid maximum: the largest value on the 8 corners of the visited slab (the
+        // maximum sits on the far corner for Yee-like stencils, on an axis end for smoothed ones like Lehe's)
+        double probe = 0.;
+        for (int q = 1; q < 8; ++q) {
+            const int xc = (q & 1) ? a.x_end - 1 : a.x_begin, yc = (q & 2) ? g.ny - 1 : 0, zc = (q & 4) ? g.nz - 1 : 0;
+            probe = fmax(probe, sqrtarg_exact_at<UNIT>(&c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc],
+                                                       g.sz2[zc], g.Y2, g.rY2, g.Z2, g.rZ2));
+        }
+        const bool sane = (mb <= 16. * probe) && (c.c2dt.x * mb <= 134217728.);
         if (!sane) atomicOr(&s_force, 1);
     }
     __syncthreads();
@@ -185,7 +193,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll 1
             for (int yy = (nit - 1) * U; yy >= 0; yy -= U, row -= U * ROW) {
                 // W = 2 dt^2 A (regrouped), v = W - 1 = 2 s^2 - 1, t = v^2, hk = pi/2 - k dt
-                double W[J], A[J], v[J], t[J], e[J], hk[J], w[U];
+                double W[J], A[J], v[J], t[J], e[J], hk[J], w[U], kr[U];
                 bool need = false, all_mid = true;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -196,6 +204,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                     // |k| (dispersion.py:350) to 1 ulp: its rounding enters (omega - k) like omega's own
                     // (2.8e-15) and far below it; the correctly rounded version costs 4 more instructions per row
                     const double k = sqrt_approx(__dadd_rn(yk.y, kz2));
+                    kr[u] = k;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const int j = u * C + c;
@@ -252,25 +261,39 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
                 } else {
-                    if (!redone) {
-                        // v <= -1 + 2^-21 (sqrtarg may be negative), v >= 1 - 2^-9 - 2^-12 (EXACT class), NaN
-                        need = false;
+                    // -1 + 2^-21 < v < -1/2 on every lane and chain: the LOW class, out of reach of every guard
+                    bool low_safe = true;
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        low_safe = low_safe && ((unsigned int)__double2hiint(v[j]) - 0xbfe00001u <= 0x000ffffdu);
+                    if (__all_sync(FULL, low_safe)) {
+                        // dt*omega = 2 s f(s^2), s^2 = dt^2 A = W/2; minus k dt taken directly (see scaled_dev_nonmid)
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
-                            const int hv = __double2hiint(v[j]);
-                            need = need || ((unsigned int)hv >= 0xbfefffffu) || (hv >= 0x3fefee00);
+                            const double z2 = __dmul_rn(W[j], 0.5);
+                            e[j] = fma(-kr[j / C], dtc[j % C], __dmul_rn(__dmul_rn(sqrt_approx(z2), 2.0), asin_f(z2)));
                         }
-                        if (__any_sync(FULL, need)) {
-                            redo_exact();
-                        } else {
+                    } else {
+                        if (!redone) {
+                            // v <= -1 + 2^-21 (sqrtarg may be negative), v >= 1 - 2^-9 - 2^-12 (EXACT class), NaN
+                            need = false;
 #pragma unroll
-                            for (int j = 0; j < J; ++j) A[j] = W[j];   // never read: no lane is in the EXACT class
+                            for (int j = 0; j < J; ++j) {
+                                const int hv = __double2hiint(v[j]);
+                                need = need || ((unsigned int)hv >= 0xbfefffffu) || (hv >= 0x3fefee00);
+                            }
+                            if (__any_sync(FULL, need)) {
+                                redo_exact();
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < J; ++j) A[j] = W[j];   // never read: no lane is in the EXACT class
+                            }
                         }
+                        double z2[J];
+#pragma unroll
+                        for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);
+                        scaled_dev_nonmid<C, J>(A, z2, v, hk, kr, e, cand, FULL);
                     }
-                    double z2[J];
-#pragma unroll
-                    for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);
-                    scaled_dev_nonmid<C, J>(A, z2, v, hk, e, cand, FULL);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {

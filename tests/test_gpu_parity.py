@@ -455,6 +455,44 @@ def test_fuzz_against_the_c_oracle(sb):
     assert n_omega >= 20
 
 
+def test_guarded_regrouping_of_sqrtarg_on_hostile_candidates(sb):
+    """The objective kernel evaluates sqrtarg regrouped (3 instructions) and falls back to the reference's
+    operation order where the extrema, the sign or the CFL class could depend on the last bits -- and for
+    whole candidates whose coefficients defeat its error bound (csrc/objective_fa.cuh).  Raw coefficient rows
+    that aim at every guard: cancellation, plateaus, zero and negative corners, huge and tiny dt."""
+    rng = np.random.default_rng(77)
+    yee = np.array([0.5, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], dtype=float)
+    rows = [yee]
+    r = yee.copy(); r[1:4] = 0.0; rows.append(r)                                  # sqrtarg == 0 everywhere
+    r = yee.copy(); r[1], r[3] = 0.0, 0.0; rows.append(r)                         # plateau: depends on y only
+    r = yee.copy(); r[1:4] = [1e9, -1e9, 3.0]; r[4:10] = 1e9 * rng.standard_normal(6); rows.append(r)   # cancellation
+    r = yee.copy(); r[1:4] = [-1.0, 0.5, 0.25]; rows.append(r)                    # negative towards the x corner
+    r = yee.copy(); r[10:13] = [-0.4, -0.4, -0.4]; r[1:4] += 1.2; rows.append(r)  # corner near zero: 1 + 1.2 - 3*0.4*... 
+    r = yee.copy(); r[0] = 1e-8; rows.append(r)                                   # tiny dt: everything in the LOW class
+    r = yee.copy(); r[0] = 1e4; rows.append(r)                                    # huge dt: s > 1 almost everywhere
+    r = yee.copy(); r[0] = 1.0 / np.sqrt(3.0); rows.append(r)                     # Yee ON its CFL limit (s == 1 at the corner)
+    r = yee.copy(); r[0] = np.nextafter(1.0 / np.sqrt(3.0), 1.0); rows.append(r)  # one ulp beyond
+    for _ in range(6):                                                            # wild random rows
+        r = rng.standard_normal(13) * rng.choice([1e-3, 1.0, 1e3]); r[0] = abs(r[0]) + 0.1; rows.append(r)
+    rows += [yee * 1.0, yee * 1.0]
+    co = np.stack(rows)
+    for (N, Y, Z, xr) in [(24, 1.0, 1.0, None), (33, 1.3, 0.7, None), (40, 1.0, 1.0, (0, 3)), (40, 1.0, 1.0, (17, 29))]:
+        grid = O.Grid(3, N, Y, Z)
+        with ctx_from_grid(sb, grid) as ctx:
+            S, Amin, Amax, nan = ctx.objective_batch(co) if xr is None else ctx.objective_batch(co, *xr)
+        sub = grid if xr is None else O.Grid.from_tables(
+            3, [grid.cos[0].ravel()[xr[0]:xr[1]], grid.cos[1].ravel(), grid.cos[2].ravel()],
+            [grid.s2[0].ravel()[xr[0]:xr[1]], grid.s2[1].ravel(), grid.s2[2].ravel()],
+            [grid.kcomp[0].ravel()[xr[0]:xr[1]], grid.kcomp[1].ravel(), grid.kcomp[2].ravel()], Y, Z)
+        for b in range(len(co)):
+            Sr, amin, amax, nr = O.device_contract(sub, co[b])
+            tag = (N, Y, Z, xr, b)
+            assert same_bits(Amin[b], clamp_min(amin)) and same_bits(Amax[b], max(amax, 0.0)), tag + (Amin[b], amin, Amax[b], amax)
+            assert (nan[b] > 0) == (nr > 0), tag
+            if nr == 0:
+                assert (S[b] == 0.0 == Sr) or relerr(S[b], Sr) <= TOL_S, tag + (S[b], Sr)
+
+
 def test_group_velocity_is_numpy_gradient(sb):
     """sb200_group_velocity against numpy on the SAME omega: gradient components, |vg|, vph and k bitwise
     (dispersion.py:208-220: np.gradient(omega, *dks, edge_order=2), sqrt of the sum of squares, omega/k)."""
