@@ -303,20 +303,32 @@ def run_gpu_arm(a):
     launch_evals = float(hi - lo) * float(N) ** 3
     launch_ms = kern_ms / a.steps
     achieved = launch_evals * F_ALG_3D / (launch_ms * 1e-3) / 1e12
-    traffic = None
+    traffic = inst = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("objective_kernel_dram_bytes_per_launch")
+            prof = json.load(open(tpath))
+            traffic = prof.get("objective_kernel_dram_bytes_per_launch")
+            inst = prof.get("objective_kernel_fp64_inst_per_eval")
         except Exception:
-            traffic = None
+            traffic = inst = None
     roofline = dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                     traffic=traffic, kernel="sb200::objective_kernel_fa<4,true,0>",
                     flop_per_eval=F_ALG_3D, evals_per_launch=launch_evals, launch_ms=launch_ms,
                     peak_source="DFMA microbenchmark (sb200_fp64_peak) measured in this run on this GPU; "
                                 "MEASURED_PEAKS.json has no FP64 entry",
                     peak_nominal=FP64_NOMINAL_TFLOPS, frac_of_nominal=achieved / FP64_NOMINAL_TFLOPS,
-                    note="FP64-pipe bound, not HBM or tensor: inputs are O(N) tables + 13 doubles per candidate")
+                    note="FP64-pipe bound, not HBM or tensor: inputs are O(N) tables + 13 doubles per candidate. "
+                         "`achieved` prices every evaluation at the reference formulation's 61 flop (SURVEY.md 8d); "
+                         "the kernel regroups sqrtarg and evaluates asin without a square root in the common class, "
+                         "so it EXECUTES far fewer FP64 instructions than that (see `executed`) and frac can exceed 1")
+    if inst:
+        # what the FP64 pipe really does: executed thread-instructions per evaluation (ncu, profiles/) x the
+        # evaluation rate of this run, against the measured DFMA issue rate (peak TFLOP/s / 2 flop per DFMA)
+        rate = launch_evals / (launch_ms * 1e-3) * inst
+        roofline["executed"] = dict(fp64_inst_per_eval=inst, fp64_inst_per_s=rate,
+                                    pipe_frac_of_measured=rate / (peak * 1e12 / 2.0),
+                                    source="profiles/traffic.json (ncu inst_executed by opcode of the bench's own launch)")
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:

@@ -8,6 +8,8 @@ Device contract for the extrema: Amin = min(sqrtarg U {+0}), Amax = max(sqrtarg 
 exactly 0 at k = 0, so for any x-range containing plane 0 these are numpy's min / max up to the sign
 of zero.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -491,6 +493,79 @@ def test_guarded_regrouping_of_sqrtarg_on_hostile_candidates(sb):
             assert (nan[b] > 0) == (nr > 0), tag
             if nr == 0:
                 assert (S[b] == 0.0 == Sr) or relerr(S[b], Sr) <= TOL_S, tag + (S[b], Sr)
+
+
+_VARIANT_SCRIPT = """
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import optimize_stencil_b200 as sb
+z = np.load(%(inp)r)
+out = {}
+for i in range(int(z['ncase'])):
+    cos, s2, kc = [[z['c%%d_%%s%%d' %% (i, n, a)] for a in range(3)] for n in ('cos', 's2', 'kc')]
+    with sb.Context(3, cos, s2, kc, Y=float(z['c%%d_Y' %% i]), Z=float(z['c%%d_Z' %% i])) as ctx:
+        if 'c%%d_w' %% i in z.files:
+            ctx.set_weight(z['c%%d_w' %% i])
+        xr = z['c%%d_xr' %% i]
+        S, lo, hi, nan = ctx.objective_batch(z['c%%d_co' %% i], int(xr[0]), int(xr[1]))
+        out['S%%d' %% i], out['lo%%d' %% i], out['hi%%d' %% i], out['nan%%d' %% i] = S, lo, hi, nan
+np.savez(%(outp)r, **out)
+"""
+
+
+def test_regrouped_kernel_agrees_with_the_reference_order_kernel(sb, tmp_path):
+    """Differential test of csrc/objective_fa.cuh against the SAME library built with -DSB200_FAST_A=0 (sqrtarg in
+    the reference's operation order at every k-point, libstencil_b200_reforder.so, loaded in a subprocess through
+    SB200_LIB): extrema and NaN flags bit for bit, sums to 1e-13, on feasible, on-CFL, infeasible and hostile
+    candidates, unit and non-unit cells, weights and x-slabs."""
+    import subprocess
+    import sys
+    from optimize_stencil_b200 import _build
+    assert os.path.exists(_build.LIB_REFORDER), "run __graft_entry__.build() first: " + _build.LIB_REFORDER
+    rng = np.random.default_rng(31)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    dlx = 0.25 * (1 - 1 / 0.96 ** 2 * np.sin(np.pi * 0.96 / 2.0))
+    lehe = np.array([0.96, .125, .125, .125, .125, .125, .125, dlx, 0.0, 0.0])
+    P = np.concatenate([xc + 1e-3 * rng.standard_normal((40, 10)), lehe + 1e-5 * rng.standard_normal((24, 10)),
+                        xc + 0.3 * rng.standard_normal((40, 10)), 3.0 * rng.standard_normal((16, 10))])
+    P[64:, 0] = np.abs(P[64:, 0]) + 0.05
+    co = np.stack([O.coefficients("StencilFree3D", p) for p in P])
+    cases = [(64, 1.0, 1.0, None, (0, 64)), (50, 1.3, 0.8, None, (0, 50)), (48, 1.0, 1.0, "plane", (0, 48)),
+             (40, 0.9, 1.0, "dense", (0, 40)), (64, 1.0, 1.0, None, (5, 23)), (33, 1.0, 1.0, None, (30, 33))]
+    inp = dict(ncase=len(cases))
+    for i, (N, Y, Z, wk, xr) in enumerate(cases):
+        grid = O.Grid(3, N, Y, Z)
+        cos, s2, kc = grid.flat_tables()
+        for a in range(3):
+            inp["c%d_cos%d" % (i, a)], inp["c%d_s2%d" % (i, a)], inp["c%d_kc%d" % (i, a)] = cos[a], s2[a], kc[a]
+        inp["c%d_Y" % i], inp["c%d_Z" % i], inp["c%d_co" % i], inp["c%d_xr" % i] = Y, Z, co, np.array(xr)
+        if wk == "plane":
+            inp["c%d_w" % i] = rng.random((1, N, N))
+        elif wk == "dense":
+            inp["c%d_w" % i] = rng.random((N, N, N))
+    np.savez(tmp_path / "in.npz", **inp)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, lib in (("fast", None), ("ref", _build.LIB_REFORDER)):
+        env = dict(os.environ)
+        env.pop("SB200_LIB", None)
+        if lib:
+            env["SB200_LIB"] = lib
+        outp = str(tmp_path / (tag + ".npz"))
+        script = _VARIANT_SCRIPT % dict(root=root, inp=str(tmp_path / "in.npz"), outp=outp)
+        subprocess.run([sys.executable, "-c", script], env=env, check=True, timeout=600)
+        res[tag] = np.load(outp)
+    n_finite = 0
+    for i in range(len(cases)):
+        f, r = res["fast"], res["ref"]
+        assert np.array_equal(f["lo%d" % i].view(np.int64), r["lo%d" % i].view(np.int64)), cases[i]
+        assert np.array_equal(f["hi%d" % i].view(np.int64), r["hi%d" % i].view(np.int64)), cases[i]
+        assert np.array_equal(f["nan%d" % i] > 0, r["nan%d" % i] > 0), cases[i]
+        ok = r["nan%d" % i] == 0
+        assert np.array_equal(np.isnan(f["S%d" % i]), np.isnan(r["S%d" % i]))
+        assert np.max(relerr(f["S%d" % i][ok], r["S%d" % i][ok])) <= 1e-13, cases[i]
+        n_finite += int(ok.sum())
+    assert n_finite >= 300
 
 
 def test_group_velocity_is_numpy_gradient(sb):
