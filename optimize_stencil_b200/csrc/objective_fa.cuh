@@ -19,7 +19,8 @@
 // A lane asks for the exact value
 //   (1) when the high word of W' reaches thr = high word of (2 dt^2 * the thread's running exact maximum) - 2
 //       -- ONE signed integer compare per evaluation, the only extra work in the common (MID) path;
-//   (2,3) outside the MID class only: v <= -1 + 2^-21, v >= 1 - 2^-9 - 2^-12 or NaN.
+//   (2,3) outside the MID class only: v <= -1 + 2^-21 (or a sign-bit NaN), 1 - 2^-9 - 2^-12 <= v < 1 + 2^-12
+//       (beyond that s > 1 and omega is NaN whatever the last bits of sqrtarg are).
 // If any lane of the warp asks, the whole iteration is redone from the tables in the reference's order
 // (sqrtarg_exact_at) and only those exact values feed the extrema.  With rows walked from high x, y to low
 // this happens about once per plane.
@@ -275,18 +276,20 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                         }
                     } else {
                         if (!redone) {
-                            // v <= -1 + 2^-21 (sqrtarg may be negative), v >= 1 - 2^-9 - 2^-12 (EXACT class), NaN
+                            // v <= -1 + 2^-21 (sqrtarg may be negative or a negative NaN) or v within
+                            // [1 - 2^-9 - 2^-12, 1 + 2^-12): the EXACT class needs the reference's bits there.
+                            // Beyond 1 + 2^-12 it does not: s > 1 and omega is NaN whatever the last bits are.
                             need = false;
 #pragma unroll
                             for (int j = 0; j < J; ++j) {
-                                const int hv = __double2hiint(v[j]);
-                                need = need || ((unsigned int)hv >= 0xbfefffffu) || (hv >= 0x3fefee00);
+                                const unsigned int hv = (unsigned int)__double2hiint(v[j]);
+                                need = need || (hv >= 0xbfefffffu) || (hv - 0x3fefee00u < 0x1300u);
                             }
                             if (__any_sync(FULL, need)) {
                                 redo_exact();
                             } else {
 #pragma unroll
-                                for (int j = 0; j < J; ++j) A[j] = W[j];   // never read: no lane is in the EXACT class
+                                for (int j = 0; j < J; ++j) A[j] = __dmul_rn(W[j], cand[j % C].ic2);   // read where s > 1 only
                             }
                         }
                         double z2[J];
