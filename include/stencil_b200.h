@@ -106,7 +106,8 @@ int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, int64_t coun
  * for the whole grid).  Outputs are HOST arrays of nbatch entries each:
  *   S[b]    = sum over the visited points of w * (omega - k)^2       (NaN if any omega is NaN)
  *   Amin[b] = min(sqrtarg U {+0}),  Amax[b] = max(sqrtarg U {+0})  over the visited points, bit-exact:
- *             sqrtarg is evaluated in the reference's operation order without FMA contraction.
+ *             every value that can be an extremum is evaluated in the reference's operation order without
+ *             FMA contraction (sb200_export does so at every point).
  *             sqrtarg is exactly 0 at k = 0, so for any range containing plane 0 these ARE
  *             numpy.min / numpy.max of the reference's array (up to the sign of a zero).  All the
  *             reference needs (dispersion.py:292-302, 149) is "is the minimum negative, and if so
