@@ -461,14 +461,24 @@ static int export_device_impl(sb200_ctx* ctx, const double* coeffs_host, int wha
     CUDA_TRY(ctx, cudaStreamSynchronize(st));  // the pinned staging row may still be in flight
     memcpy(ctx->h_pin, coeffs_host, ctx->ncoef * sizeof(double));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coeffs, ctx->h_pin, ctx->ncoef * sizeof(double), cudaMemcpyHostToDevice, st));
-    const size_t total = (size_t)(xe - xb) * ctx->g.ny * ctx->g.nz;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    const int threads = std::min(256, ((ctx->g.nz + 31) / 32) * 32);
+    const int n_ztiles = (ctx->g.nz + threads - 1) / threads;
+    const int n_ytiles = (ctx->g.ny + EXPORT_ROWS - 1) / EXPORT_ROWS;
+    const long long ntiles = (long long)(xe - xb) * n_ytiles * n_ztiles;
+    const int blocks = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);   // persistent: 8 CTAs per SM
     if ((rc = grow(ctx, (unsigned char**)&ctx->d_part, &ctx->d_part_cap, (size_t)blocks * 3 * 8))) return rc;
     ExportArgs a;
     a.coeffs = ctx->d_coeffs; a.ncoef = ctx->ncoef; a.what = what; a.x_begin = xb; a.x_end = xe;
+    a.n_ytiles = n_ytiles; a.n_ztiles = n_ztiles;
     a.out = d_out; a.part = (unsigned long long*)ctx->d_part; a.ticket = ctx->d_xticket; a.stats = d_stats;
-    if (ctx->unit_cell) export_kernel<true><<<blocks, 256, 0, st>>>(ctx->g, a);
-    else export_kernel<false><<<blocks, 256, 0, st>>>(ctx->g, a);
+#define SB200_EXPORT(UNIT)                                                                  \
+    do {                                                                                    \
+        if (what == SB200_X_OMEGA) export_kernel<UNIT, 0><<<blocks, threads, 0, st>>>(ctx->g, a);        \
+        else if (what == SB200_X_SQRTARG) export_kernel<UNIT, 1><<<blocks, threads, 0, st>>>(ctx->g, a); \
+        else export_kernel<UNIT, 2><<<blocks, threads, 0, st>>>(ctx->g, a);                 \
+    } while (0)
+    if (ctx->unit_cell) SB200_EXPORT(true); else SB200_EXPORT(false);
+#undef SB200_EXPORT
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SB200_ECUDA, "export kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches += 1;
