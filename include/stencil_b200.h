@@ -26,7 +26,9 @@
  *   - every call returns 0 on success, a negative SB200_E* code otherwise; the text is available
  *     from sb200_last_error().  No C++ exception crosses the ABI.  There is NO CPU fallback:
  *     without a CUDA device every compute entry point fails with SB200_ECUDA.
- *   - a context is not re-entrant: one context per host thread.
+ *   - a context is not re-entrant: one context per host thread.  The asynchronous *_device entry points
+ *     share the context's scratch buffers (partial-sum slots, tickets): issue them on ONE stream, or
+ *     synchronise between calls that use different streams.
  *   - coefficient vectors are in the reference's own field order (stencil.py:209, :275):
  *       dim 2:  dt, alphax, alphay, betaxy, betayx, deltax, deltay                     (7 doubles)
  *       dim 3:  dt, alphax, alphay, alphaz, betaxy, betaxz, betayx, betayz, betazx,
