@@ -4,7 +4,6 @@ Every test runs twice: on CPU with the oracle-backed context injected (tests/fak
 check the host logic, and under `-m gpu` against the real CUDA context.  Expected
 values come from the fixtures the unmodified reference produced (oracle/make_golden.py).
 """
-import itertools
 import pickle
 import types
 

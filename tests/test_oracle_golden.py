@@ -4,7 +4,6 @@ This is what pins the oracle: SURVEY.md 8(c) -- no reference test pins a numeric
 omega, so parity is anchored on outputs of the reference itself run in the build container.
 """
 import numpy as np
-import pytest
 
 import np_oracle as O
 from conftest import relerr

@@ -2,7 +2,6 @@
 logic of optimize_stencil_b200/sharding.py with the oracle injected as the local evaluator."""
 import os
 import socket
-import sys
 
 import numpy as np
 import pytest
