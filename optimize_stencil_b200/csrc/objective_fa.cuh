@@ -107,9 +107,11 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         Cand& c = cand[tid];
         load_candidate(c, a.coeffs + b * a.ncoef, a.ncoef);
         // Are the guards of the header sufficient for this candidate?  (every test is false for NaNs)
-        const double mb = (fabs(c.ax) + 3. * fabs(c.dlx) + fabs(c.bxy2) + fabs(c.bxz2)) +
-                          (fabs(c.ay) + 3. * fabs(c.dly) + fabs(c.byx2) + fabs(c.byz2)) * rY +
-                          (fabs(c.az) + 3. * fabs(c.dlz) + fabs(c.bzx2) + fabs(c.bzy2)) * rZ;
+        // Mbound: |cos| <= 1, |1 + 2 cos| <= 3, 0 <= s2 <= 1 for the reference's tables; tab_scale covers a
+        // caller who hands over anything else (it is 1 otherwise, NaN for NaN tables)
+        const double mb = ((fabs(c.ax) + 3. * fabs(c.dlx) + fabs(c.bxy2) + fabs(c.bxz2)) +
+                           (fabs(c.ay) + 3. * fabs(c.dly) + fabs(c.byx2) + fabs(c.byz2)) * rY +
+                           (fabs(c.az) + 3. * fabs(c.dlz) + fabs(c.bzx2) + fabs(c.bzy2)) * rZ) * g.tab_scale;
         // a lower bound of the grid maximum: the largest value on the 8 corners of the visited slab (the
         // maximum sits on the far corner for Yee-like stencils, on an axis end for smoothed ones like Lehe's)
         double probe = 0.;

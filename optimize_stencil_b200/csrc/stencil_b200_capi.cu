@@ -141,6 +141,7 @@ static int create_impl(sb200_ctx* ctx, const sb200_grid_desc* d) {
     for (int a = 0; a < d->dim; ++a) n3[a + off] = d->n[a];
     std::vector<double> host;
     size_t offs[9];
+    double amax[2] = {1.0, 1.0};      // max(1, max|cos|), max(1, max|s2|); NaN-sticky
     for (int t = 0; t < 3; ++t)       // 0 cos, 1 s2, 2 k^2
         for (int a = 0; a < 3; ++a) {
             offs[t * 3 + a] = host.size();
@@ -153,6 +154,7 @@ static int create_impl(sb200_ctx* ctx, const sb200_grid_desc* d) {
                     else if (t == 1) v = d->s2[ua][i];
                     else v = d->kcomp[ua][i] * d->kcomp[ua][i];  // dispersion.py:276, 350 (x**2)
                 }
+                if (t < 2 && amax[t] == amax[t] && !(std::fabs(v) <= amax[t])) amax[t] = std::fabs(v);   // |NaN| = NaN sticks
                 host.push_back(v);
             }
             while (host.size() % 2) host.push_back(0.0);  // keep 16-byte alignment per table
@@ -173,6 +175,7 @@ static int create_impl(sb200_ctx* ctx, const sb200_grid_desc* d) {
     g.rY2 = 1.0 / g.Y2;   // IEEE division on the host: the correctly rounded reciprocals div_invariant needs
     g.rZ2 = 1.0 / g.Z2;
     ctx->unit_cell = (g.Y2 == 1.0 && g.Z2 == 1.0);
+    g.tab_scale = amax[0] * amax[1];   // 1 for genuine cos / s2 tables; widens the regrouping error bound otherwise
     g.w = nullptr;
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));

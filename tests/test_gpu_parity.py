@@ -495,6 +495,29 @@ def test_guarded_regrouping_of_sqrtarg_on_hostile_candidates(sb):
                 assert (S[b] == 0.0 == Sr) or relerr(S[b], Sr) <= TOL_S, tag + (S[b], Sr)
 
 
+def test_tables_that_are_not_cosines(sb):
+    """The C-ABI takes the per-axis tables from the caller.  Tables outside [-1, 1] / [0, 1] widen the error
+    bound of the regrouped sqrtarg (GridDev::tab_scale); the extrema must stay the oracle's bits."""
+    rng = np.random.default_rng(5)
+    N = 21
+    base = O.Grid(3, N)
+    cos = [3.0 * c.ravel() + 0.1 * rng.standard_normal(N) for c in base.cos]
+    s2 = [2.5 * t.ravel() * (1 + 0.2 * rng.random(N)) for t in base.s2]
+    kc = [k.ravel().copy() for k in base.kcomp]
+    grid = O.Grid.from_tables(3, cos, s2, kc)
+    xc = np.array([0.2, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    co = np.stack([O.coefficients("StencilFree3D", xc + 0.05 * rng.standard_normal(10)) for _ in range(9)])
+    with sb.Context(3, cos, s2, kc) as ctx:
+        S, Amin, Amax, nan = ctx.objective_batch(co)
+        np.testing.assert_array_equal(ctx.export(co[0], 1)[0], O.sqrtarg(grid, co[0]))
+    for b in range(len(co)):
+        Sr, amin, amax, nr = O.device_contract(grid, co[b])
+        assert same_bits(Amin[b], clamp_min(amin)) and same_bits(Amax[b], max(amax, 0.0)), b
+        assert (nan[b] > 0) == (nr > 0), b
+        if nr == 0:
+            assert relerr(S[b], Sr) <= TOL_S, (b, S[b], Sr)
+
+
 _VARIANT_SCRIPT = """
 import sys, numpy as np
 sys.path.insert(0, %(root)r)
