@@ -264,19 +264,11 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
                 } else {
-                    // -1 + 2^-21 < v < -1/2 on every lane and chain: the LOW class, out of reach of every guard
-                    bool low_safe = true;
+                    double z2[J];
 #pragma unroll
-                    for (int j = 0; j < J; ++j)
-                        low_safe = low_safe && ((unsigned int)__double2hiint(v[j]) - 0xbfe00001u <= 0x000ffffdu);
-                    if (__all_sync(FULL, low_safe)) {
-                        // dt*omega = 2 s f(s^2), s^2 = dt^2 A = W/2; minus k dt taken directly (see scaled_dev_nonmid)
-#pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            const double z2 = __dmul_rn(W[j], 0.5);
-                            e[j] = fma(-kr[j / C], dtc[j % C], __dmul_rn(__dmul_rn(sqrt_approx(z2), 2.0), asin_f(z2)));
-                        }
-                    } else {
+                    for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);             // dt^2 A
+                    // |v| <= sqrt(3)/2, or -1 + 2^-21 < v < -1/2, on every lane and chain: out of reach of every guard
+                    if (!dev_try_nosqrt<C, J>(v, hk, e, FULL) && !dev_try_low<C, J, true>(z2, v, kr, e, cand, FULL)) {
                         if (!redone) {
                             // v <= -1 + 2^-21 (sqrtarg may be negative or a negative NaN) or v within
                             // [1 - 2^-9 - 2^-12, 1 + 2^-12): the EXACT class needs the reference's bits there.
@@ -289,15 +281,14 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                             }
                             if (__any_sync(FULL, need)) {
                                 redo_exact();
+#pragma unroll
+                                for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < J; ++j) A[j] = __dmul_rn(W[j], cand[j % C].ic2);   // read where s > 1 only
                             }
                         }
-                        double z2[J];
-#pragma unroll
-                        for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);
-                        scaled_dev_nonmid<C, J>(A, z2, v, hk, kr, e, cand, FULL);
+                        dev_high_or_any<C, J>(A, z2, v, hk, kr, e, cand, FULL);
                     }
                 }
 #pragma unroll
