@@ -10,11 +10,16 @@ constraints and options, optimize.py:136,142).  What changes is the data-paralle
              feasibility of every start), and inside each search one launch serves the objective,
              both constraints and all their finite-difference points of an iterate (see
              dispersion.py).  `--singlecore` is accepted and changes nothing by default.
-             What remains is SciPy's own per-iteration Python overhead; for big start grids it can be
-             spread over worker processes that share the GPU (`args.workers = N` or the environment
-             variable OPTSTENCIL_WORKERS=N; every worker re-creates its device context lazily, exactly
-             like the reference's pickled Dispersion objects re-run init2).  Each start is independent
-             and deterministic, so the result does not depend on the number of workers.
+             SLSQP is handed the forward differences it would take itself as `jac` callables and the
+             constraint list stacked into one vector-valued constraint (`exact_fd_jac`: same points, same
+             arithmetic, same rows -- the search is bit-identical, the Python overhead per iterate drops 3x).
+             What remains is SciPy's own per-iteration Python time.  It can be spread over worker processes
+             that share the GPU (`args.workers = N` or the environment variable OPTSTENCIL_WORKERS=N; every
+             worker re-creates its device context lazily, exactly like the reference's pickled Dispersion
+             objects re-run init2; each start is independent and deterministic, so the result does not depend
+             on the number of workers) -- but measured on one B200 without MPS this does not pay: the
+             workers' small launches time-slice the device (4096 starts on 128^3: 29.7 s in-process, 31.5 s
+             with 8 workers, tools/workers_timing.py), so it stays opt-in.
 
 The printed lines keep the reference's format (optimize.py:71, 144, 191, 200-202).
 """

@@ -15,11 +15,13 @@ if __name__ == "__main__":
                 deltazrange=[-1, 0.25], betaxyrange=[-1, 1], betaxzrange=[-1, 1], betayxrange=[-1, 1],
                 betayzrange=[-1, 1], betazxrange=[-1, 1], betazyrange=[-1, 1], dtrange=[0.3, 0.6], weight="equal",
                 weight_params=[], singlecore=False)
-    for w in (0, 4, 8):
+    if len(sys.argv) > 1 and sys.argv[1] == "config3":      # 4096 (dt, delta) starts on 128^3, 2 free parameters
+        base.update(N=64, Ngrid_low=128, Ngrid_high=128, dtrange=[0.6718, 1.0])
+    for w in (0, 8, 16):
         a = types.SimpleNamespace(workers=w, **base)
         with contextlib.redirect_stdout(io.StringIO()):
             opt = es.Optimize(a)
             t = time.perf_counter()
             x, f = opt.optimize()
             el = time.perf_counter() - t
-        print("3D div-free 48^3, 36 starts, workers=%d: %.2f s  x=%s norm=%r" % (w, el, x, f), flush=True)
+        print("3D div-free %d^3, N=%d, workers=%d: %.2f s  x=%s norm=%r" % (base["Ngrid_low"], base["N"], w, el, x, f), flush=True)
