@@ -59,6 +59,7 @@ class Dispersion:
         self._w_dirty = True
         self._ctx = None
         self._cache = {}
+        self._fd_last = None
         self._k = None
         self.init2_run = False
         self.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
@@ -100,6 +101,7 @@ class Dispersion:
         state['_ctx'] = None
         state['_w_dirty'] = True
         state['_cache'] = {}
+        state['_fd_last'] = None
         return state
 
     # -- weight function ------------------------------------------------------------------------
@@ -118,6 +120,7 @@ class Dispersion:
         """Tell the object that `w` was modified in place: re-upload it and drop cached results."""
         self._w_dirty = True
         self._cache.clear()
+        self._fd_last = None
 
     # -- device context ---------------------------------------------------------------------------
     def _context(self):
@@ -334,32 +337,52 @@ class Dispersion:
     def _dt_ok_of(self, e, p):
         return -1. if e is None else self._gate(e)[1]
 
-    def _fd_jac(self, value_of, scalar_fun, x):
+    def _fd_points(self, x):
+        """(p, dx, entries) of x and its n forward-difference neighbours; memoised for the last x, because SLSQP
+        asks for the Jacobians of the objective and of every constraint at the same iterate.  dx is None
+        where SciPy would switch to a relative step (or x is not finite): the caller then lets SciPy do it."""
         p = np.array(x, dtype=float).ravel()
+        key = p.tobytes()
+        last = self._fd_last
+        if last is not None and last[0] == key and last[4] is self._cache:
+            return last[1], last[2], last[3]
         n = len(p)
         ph = p + FD_STEP
         dx = ph - p
         if not np.all(dx) or not np.all(np.isfinite(p)):
-            # SciPy switches to a relative step there (or the point is garbage): let it do the work
-            from scipy.optimize._numdiff import approx_derivative
-            return approx_derivative(scalar_fun, p, method='2-point', abs_step=FD_STEP)
-        e0 = self._entry(p)                                  # a miss evaluates all n + 1 points at once
+            self._fd_last = (key, p, None, None, self._cache)
+            return p, None, None
+        entries = [self._entry(p)]                           # a miss evaluates all n + 1 points at once
+        P = np.repeat(p[None, :], n, axis=0)
+        P[np.arange(n), np.arange(n)] = ph                   # row i: copy(x); x1[i] = x[i] + h
         if not self.fd_prefetch:
-            P = np.repeat(p[None, :], n, axis=0)
-            P[np.arange(n), np.arange(n)] = ph
             missing = [i for i in range(n) if P[i].tobytes() not in self._cache]
             if missing:
                 self._raw_batch(np.ascontiguousarray(P[missing]))
-        f0 = value_of(e0, p)
+        entries += [self._entry(P[i]) for i in range(n)]
+        self._fd_last = (key, p, dx.tolist(), entries, self._cache)
+        self._fd_last_point = P[n - 1]
+        return p, self._fd_last[2], entries
+
+    def _fd_jac(self, value_of, scalar_fun, x):
+        p, dx, entries = self._fd_points(x)
+        if dx is None:
+            # SciPy switches to a relative step there (or the point is garbage): let it do the work
+            from scipy.optimize._numdiff import approx_derivative
+            return approx_derivative(scalar_fun, p, method='2-point', abs_step=FD_STEP)
+        n = len(p)
+        f0 = value_of(entries[0], p)
         J = np.empty(n)
-        x1 = p.copy()
-        dxl = dx.tolist()
         for i in range(n):
-            x1[i] = ph[i]
-            J[i] = (value_of(self._entry(x1), x1) - f0) / dxl[i]
-            x1[i] = p[i]
-        x1[n - 1] = ph[n - 1]
-        self.parameters = x1                                 # the last point the reference would have seen
+            e = entries[i + 1]
+            if e is None or e[3]:                            # the value may raise: give it the right point
+                x1 = p.copy()
+                x1[i] = p[i] + FD_STEP
+                fi = value_of(e, x1)
+            else:
+                fi = value_of(e, None)
+            J[i] = (fi - f0) / dx[i]
+        self.parameters = self._fd_last_point                # the last point the reference would have seen
         return J
 
     def norm_fd(self, parameters):
