@@ -99,7 +99,6 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     const int xs = a.x_begin + blockIdx.y * a.tile_x;
     const int xe = min(xs + a.tile_x, a.x_end);
     const int ys = blockIdx.z * a.tile_y;
-    const int ye = min(ys + a.tile_y, g.ny);
     const long long b0 = (long long)chunk * C;
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
 
@@ -153,12 +152,12 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const bool active = zraw < g.nz;
         if (__ballot_sync(FULL, active) == 0u) continue;                  // warp-uniform
         const int z = min(zraw, g.nz - 1);
-        const double cx = g.cx[x], sx2 = g.sx2[x], kx2 = g.kx2[x];
-        const double opx = __dadd_rn(1.0, __dmul_rn(2.0, cx));
         const double cz = g.cz[z];
         const double sz2r = __dmul_rn(g.sz2[z], rZ);
         const double kz2 = g.kz2[z];
         const double opz = __dadd_rn(1.0, __dmul_rn(2.0, cz));
+        {
+            const double cx = g.cx[x], sx2 = g.sx2[x];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const double c2 = cand[c].c2dt.x;
@@ -167,11 +166,21 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
             tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
             Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
         }
+        }
+        int bz = blockIdx.z;                               // (opaque copy: the end of the y range is re-derived per
+        asm volatile("" : "+r"(bz));                       //  plane instead of being held, or spilled, across the sweep)
+        const int ye = min(bz * a.tile_y + a.tile_y, g.ny);
         for (int y1 = ye; y1 > ys; y1 -= ROWS) {          // y tiles from the top of the range downwards
             const int y0 = max(ys, y1 - ROWS);
             const int nrows = y1 - y0;
             __syncwarp();                      // every lane is done reading the previous tile
             {                                  // lane l builds row l
+                // the x-dependent table entries are re-read here (L1 hits) through an opaque index rather
+                // than kept in 8 registers across the sweep of the previous tile
+                int xq = x;
+                asm volatile("" : "+r"(xq));
+                const double cx = g.cx[xq], sx2 = g.sx2[xq], kx2 = g.kx2[xq];
+                const double opx = __dadd_rn(1.0, __dmul_rn(2.0, cx));
                 const int y = min(y0 + lane, y1 - 1);   // rows past the tile's end repeat its last row
                 const double cy = g.cy[y];
                 const double opy = __dadd_rn(1.0, __dmul_rn(2.0, cy));
@@ -227,9 +236,10 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                 // Rare: redo the iteration in the reference's operation order and let the exact values (and
                 // only those) into the extrema.  The opaque copies keep the address arithmetic in here.
                 auto redo_exact = [&]() {
-                    int zq = z, yq = yy;
-                    asm volatile("" : "+r"(zq), "+r"(yq));
+                    int zq = z, yq = yy, xq = x;
+                    asm volatile("" : "+r"(zq), "+r"(yq), "+r"(xq));
                     const double czr = ld_rare(g.cz + zq), sz2 = ld_rare(g.sz2 + zq);
+                    const double cx = ld_rare(g.cx + xq), sx2 = ld_rare(g.sx2 + xq);
                     all_mid = true;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -316,7 +326,10 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         um[c] = s_umax[c * blockDim.x + tid];
         sm[c] = s_smax[c * blockDim.x + tid];
     }
-    finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk, ztile, b0);
+    int bx = blockIdx.x;                                   // re-derived from an opaque copy: chunk / ztile / b0 need not stay alive
+    asm volatile("" : "+r"(bx));
+    const int chunk_e = bx / a.n_ztiles;
+    finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk_e, bx - chunk_e * a.n_ztiles, (long long)chunk_e * C);
 }
 
 }  // namespace sb200
