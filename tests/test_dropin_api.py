@@ -293,6 +293,47 @@ def test_fd_jacobians_equal_scipy_approx_derivative(es):
                 np.testing.assert_array_equal(con.jac(p), approx_derivative(con, p, method="2-point", abs_step=FD_STEP))
 
 
+def test_stacked_constraints_are_the_reference_list_row_for_row(es):
+    """optimize.py: _stacked_constraints hands SLSQP the reference's scalar constraints (optimize.py:96-110) as one
+    vector; values and forward-difference normals must be those of the list, row for row, bit for bit -- also
+    where SciPy falls back to a relative step (x_i + h == x_i) and on a bound."""
+    from scipy.optimize._numdiff import approx_derivative
+    from optimize_stencil_b200.extended_stencil.dispersion import FD_STEP
+    from optimize_stencil_b200.extended_stencil.optimize import _stacked_constraints
+    monkey = dict(exact_fd_jac=es.Optimize.exact_fd_jac)
+    es.Optimize.exact_fd_jac = False
+    try:
+        opt = es.Optimize(default_args(Ngrid_low=20, Ngrid_high=20))
+    finally:
+        es.Optimize.exact_fd_jac = monkey["exact_fd_jac"]
+    cons = opt.constraints                                    # the reference's list: no 'jac' keys
+    assert len(cons) == 2 + 2 * len(opt.stencil.Parameters._fields) and "jac" not in cons[0]
+    stacked = _stacked_constraints(opt.dispersion, cons)
+    pts = [np.array([0.5, 0.05, -0.02, -0.1]), np.array([1.0, -1.0, 0.25, -1.0]),      # on the bounds
+           np.array([0.5, 0.05, -0.02, 1e9]), np.array([0.3, 0.0, -0.0, 0.1])]          # relative-step fallback, zeros
+    with np.errstate(all="ignore"):
+        for p in pts:
+            want = np.concatenate([np.atleast_1d(np.asarray(c["fun"](p), dtype=float)) for c in cons])
+            np.testing.assert_array_equal(stacked.fun(p), want)
+            J = np.vstack([np.atleast_2d(approx_derivative(c["fun"], p, method="2-point", abs_step=FD_STEP)) for c in cons])
+            np.testing.assert_array_equal(stacked.jac(p), J)
+
+
+def test_fd_memo_follows_the_weight(es):
+    """The finite-difference points of the last iterate are memoised; a new weight must drop them."""
+    d = es.Dispersion2D(1, 24, es.StencilSymmetric2D())
+    x = np.array([0.5, 0.05, -0.05, -0.04])
+    g1 = d.norm_fd(x)
+    np.testing.assert_array_equal(d.norm_fd(x), g1)
+    launches = d.stats["launches"]
+    d.stencil_ok_fd(x), d.dt_ok_fd(x)
+    assert d.stats["launches"] == launches                   # all three Jacobians from one launch
+    d.w = 2.0
+    g2 = d.norm_fd(x)
+    assert d.stats["launches"] == launches + 1
+    assert np.max(np.abs(g2 - 2 * g1)) <= 1e-6 * np.max(np.abs(g1))   # differences of doubled sums: same to FD noise
+
+
 def test_start_grid(es):
     opt = es.Optimize(default_args(N=2, scan_dt=False))
     starts = opt.start_grid()
