@@ -157,15 +157,15 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const double kz2 = g.kz2[z];
         const double opz = __dadd_rn(1.0, __dmul_rn(2.0, cz));
         {
-            const double cx = g.cx[x], sx2 = g.sx2[x];
+            const double cx = g.cx[x], sx2 = g.sx2[x];   // needed here only: the row builder re-reads them
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const double c2 = cand[c].c2dt.x;
-            const double tzx = __dmul_rn(cand[c].bxz2, cz);
-            const double tzzx = fma(cand[c].bzx2, cx, fma(cand[c].dlz, opz, cand[c].az));
-            tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
-            Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
-        }
+            for (int c = 0; c < C; ++c) {
+                const double c2 = cand[c].c2dt.x;
+                const double tzx = __dmul_rn(cand[c].bxz2, cz);
+                const double tzzx = fma(cand[c].bzx2, cx, fma(cand[c].dlz, opz, cand[c].az));
+                tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
+                Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
+            }
         }
         int bz = blockIdx.z;                               // (opaque copy: the end of the y range is re-derived per
         asm volatile("" : "+r"(bz));                       //  plane instead of being held, or spilled, across the sweep)
