@@ -281,7 +281,9 @@ size_t smem_bytes(int C, int TY, int TZ) {
 Plan make_plan(const sb200_ctx* ctx, long long B, int nxr) {
     const GridDev& g = ctx->g;
     Plan p;
-    p.C = ctx->force_c ? ctx->force_c : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));
+    // candidates per thread: 4 from B = 3 on (a padded fourth candidate costs less than the 2 x 2 layout's second
+    // pass over the tables: 52 vs 59 us for 3 x 128^3)
+    p.C = ctx->force_c ? ctx->force_c : (B >= 3 ? 4 : (B >= 2 ? 2 : 1));
     if (const char* e = getenv("SB200_FORCE_C")) {         // experiments only
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) p.C = v;
