@@ -60,6 +60,7 @@ class Dispersion:
         self._ctx = None
         self._cache = {}
         self._fd_last = None
+        self._fd_index = {}
         self._k = None
         self.init2_run = False
         self.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
@@ -199,7 +200,13 @@ class Dispersion:
         if self.fd_prefetch:
             # exactly the points scipy's approx_derivative('2-point', abs_step=FD_STEP) will ask for:
             # x0 + h_vecs[i] with h_vecs = diag(h)  (scipy/optimize/_numdiff.py, _dense_difference)
-            P = np.vstack([p[None, :], p[None, :] + np.diag(np.full(len(p), FD_STEP))])
+            # (row 0 is x itself, row i + 1 a copy of x with x[i] + h: scipy's own copies, bit for bit)
+            n = len(p)
+            idx = self._fd_index.get(n)
+            if idx is None:
+                idx = self._fd_index[n] = (np.arange(1, n + 1), np.arange(n))
+            P = np.repeat(p[None, :], n + 1, axis=0)
+            P[idx] += FD_STEP
         else:
             P = p[None, :].copy()
         self._raw_batch(P)

@@ -85,6 +85,25 @@ class Stencil:
         self._param_cols = np.array([col[f] for f in self._parameters])
         self._tie_cols = [(col[d], col[s]) for d, s in self.TIES]
         self._alpha_cols = [(col[a], [col[b] for b in betas], col[d]) for a, betas, d in self.ALPHAS]
+        # The same procedure "compiled" into a handful of array operations (coefficients_batch runs once per
+        # SLSQP iterate): the ordered copies collapse into one gather from the parameter columns, and the
+        # alphas -- which only read betas and deltas -- are evaluated side by side, element by element in the
+        # reference's own order (1 - 2 b1 [- 2 b2] - 3 d), so every coefficient keeps its bits.
+        src = [-1] * self.Coefficients._nfields
+        for k, c in enumerate(self._param_cols):
+            src[c] = k
+        for d, s_ in self._tie_cols:
+            src[d] = src[s_]
+        self._gather_dst = np.array([c for c in range(len(src)) if src[c] >= 0], dtype=int)
+        self._gather_src = np.array([src[c] for c in self._gather_dst], dtype=int)
+        acols = [a for a, _, _ in self._alpha_cols]
+        nb = {len(b) for _, b, _ in self._alpha_cols}
+        reads = {c for _, b, d in self._alpha_cols for c in list(b) + [d]}
+        self._alpha_plan = None
+        if len(nb) == 1 and not (reads & set(acols)):
+            self._alpha_plan = (np.array(acols, dtype=int),
+                                [np.array([b[k] for _, b, _ in self._alpha_cols], dtype=int) for k in range(nb.pop())],
+                                np.array([d for _, _, d in self._alpha_cols], dtype=int))
 
     @property
     def dof(self):
@@ -102,6 +121,25 @@ class Stencil:
         if P.ndim != 2 or P.shape[1] != self.dof:
             raise ValueError('{} takes {} parameters ({}), got shape {}'.format(
                 type(self).__name__, self.dof, ', '.join(self._parameters), P.shape))
+        C = np.zeros((P.shape[0], self.ncoef))
+        C[:, self._gather_dst] = P[:, self._gather_src]
+        if self._alpha_plan is not None:
+            acols, bcols, dcols = self._alpha_plan
+            acc = 1.0 - 2.0 * C[:, bcols[0]]
+            for b in bcols[1:]:
+                acc = acc - 2.0 * C[:, b]
+            C[:, acols] = acc - 3.0 * C[:, dcols]
+        else:
+            for a, betas, d in self._alpha_cols:
+                acc = 1.0 - 2.0 * C[:, betas[0]]
+                for b in betas[1:]:
+                    acc = acc - 2.0 * C[:, b]
+                C[:, a] = acc - 3.0 * C[:, d]
+        return C
+
+    def _coefficients_batch_sequential(self, params):
+        """The uncompiled procedure (ordered copies, then one alpha after the other): the check of the above."""
+        P = np.asarray(params, dtype=float).reshape(-1, self.dof)
         C = np.zeros((P.shape[0], self.ncoef))
         C[:, self._param_cols] = P
         for dst, src in self._tie_cols:
