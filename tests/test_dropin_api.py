@@ -199,6 +199,21 @@ def test_get_stencil_table(es):
     assert es.StencilSymmetric2D().Parameters._fields == ["dt", "betaxy", "deltax", "deltay"]
 
 
+def test_compiled_coefficient_fill_keeps_every_bit():
+    """Stencil.coefficients_batch runs the reference's ordered copies and alpha formulae as a few array operations;
+    it must agree bit for bit with the step-by-step procedure and with the oracle's restatement, for every family."""
+    from optimize_stencil_b200 import extended_stencil as es_
+    rng = np.random.default_rng(12)
+    for name in sorted(O.STENCILS):
+        st = getattr(es_, name)()
+        P = np.concatenate([rng.standard_normal((20, st.dof)), 1e3 * rng.standard_normal((5, st.dof)), np.zeros((1, st.dof))])
+        P[3, 0] = -0.0
+        got = st.coefficients_batch(P)
+        np.testing.assert_array_equal(got.view(np.int64), st._coefficients_batch_sequential(P).view(np.int64), err_msg=name)
+        ref = np.stack([O.coefficients(name, p) for p in P])
+        np.testing.assert_array_equal(got.view(np.int64), ref.view(np.int64), err_msg=name)
+
+
 def default_args(**over):
     base = dict(N=3, scan_dt=True, Ngrid_low=50, Ngrid_high=200, dim=2, div_free=False, symmetric_axes=0,
                 symmetric_beta=True, Y=1.0, Z=1.0, dt_multiplier=1.0, deltaxrange=[-1, 0.25],
