@@ -19,6 +19,14 @@
  *                                                                         387-399, 111-121
  *   sb200_group_velocity    <- Dispersion.omega_output / omega_interp    dispersion.py:199-232, 402-413
  *                              (numpy.gradient of omega, |vg|, vph, k on the device)
+ *   sb200_objective_batch_ex  the same with options: strided x-plane lists (load-balanced k-slabs), SEGMENTED
+ *                              batches (many independent small batches in one launch, each bit-identical to its
+ *                              own stand-alone launch: the lock-stepped multi-start scan of optimize.py:147-205)
+ *                              and the start-grid screening variant (optimize.py:118-134)
+ *   sb200_group_*           <- mp.Pool(nproc).imap(...)                  optimize.py:169-190
+ *                              (one host thread, one context per visible GPU, one stream per GPU: the batch is
+ *                               sharded by candidates or by k-slabs across the devices of ONE process,
+ *                               SURVEY.md 8b.1 "device list", 8e "process model")
  *   sb200_destroy, sb200_last_error
  *
  * Conventions
@@ -28,7 +36,9 @@
  *     without a CUDA device every compute entry point fails with SB200_ECUDA.
  *   - a context is not re-entrant: one context per host thread.  The asynchronous *_device entry points
  *     share the context's scratch buffers (partial-sum slots, tickets): issue them on ONE stream, or
- *     synchronise between calls that use different streams.
+ *     synchronise between calls that use different streams.  The host-buffer entry points run on the
+ *     context's own stream and first wait (on the device) for the last *_device call issued through this
+ *     context, so mixing the two kinds needs no host synchronisation.
  *   - coefficient vectors are in the reference's own field order (stencil.py:209, :275):
  *       dim 2:  dt, alphax, alphay, betaxy, betayx, deltax, deltay                     (7 doubles)
  *       dim 3:  dt, alphax, alphay, alphaz, betaxy, betaxz, betayx, betayz, betazx,
@@ -49,7 +59,7 @@
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 1
+#define SB200_ABI_VERSION 2
 
 /* status codes */
 #define SB200_OK        0
@@ -114,12 +124,38 @@ int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, int64_t coun
  *             numpy.min / numpy.max of the reference's array (up to the sign of a zero).  All the
  *             reference needs (dispersion.py:292-302, 149) is "is the minimum negative, and if so
  *             what is it" and the maximum when it is non-negative.  Both are NaN if any sqrtarg is.
- *   nan[b]  = 0 when no visited omega is NaN, a positive number otherwise (sb200_export returns the
- *             exact count; here it is derived from the partial sums, which a NaN omega poisons)
+ *   nan[b]  = 0 when no visited omega is NaN, a positive number otherwise.  It is a FLAG, not the count of
+ *             NaN points (SURVEY.md 8b.2 asked for a count; the reference only ever tests it against zero,
+ *             dispersion.py:193): it is derived from the partial sums, which a NaN omega poisons.
+ *             sb200_export returns the exact count.
  * Synchronous: on return the outputs are valid. */
 int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
                           int32_t x_begin, int32_t x_end,
                           double* S, double* Amin, double* Amax, int64_t* nan);
+
+/* Options of the *_ex entry points.  Zero-initialise, then set what is needed.
+ *   planes    the visited x-planes are x_begin + i * x_stride for i in [0, n_planes); n_planes == 0 means
+ *             "x_begin, x_begin + x_stride, ... while < n[0]" and x_stride == 0 means 1.  dim 2: whole grid only.
+ *   seg_size  0: one batch.  > 0: nbatch must be a multiple of seg_size; the launch then consists of
+ *             nbatch / seg_size independent SEGMENTS, and the results of every segment are bit-identical to those
+ *             of sb200_objective_batch on that segment alone (same tiling, same candidates sharing a thread, same
+ *             summation order) -- the property that lets many SLSQP searches share one launch per iterate
+ *             without changing a single search.
+ *   flags     SB200_F_SCAN: use the start-grid screening variant (a warp whose k-points all have s > 1 for all of
+ *             its candidates skips the evaluation: omega is NaN there whatever the bits).  Results are identical
+ *             to the plain variant; it is faster when most candidates violate the CFL limit and ~1.5 % slower
+ *             otherwise.  SB200_F_AUTO_SCAN (host-buffer entry points only): decide per call from the
+ *             candidates' corner values. */
+#define SB200_F_SCAN       1
+#define SB200_F_AUTO_SCAN  2
+typedef struct sb200_batch_opts {
+    int32_t x_begin, x_stride, n_planes;
+    int32_t flags;
+    int64_t seg_size;
+} sb200_batch_opts;
+
+int sb200_objective_batch_ex(sb200_ctx* ctx, const double* coeffs, int64_t nbatch, const sb200_batch_opts* opts,
+                             double* S, double* Amin, double* Amax, int64_t* nan);
 
 /* Same, with DEVICE pointers and an explicit stream: a cudaStream_t passed as void* and used
  * literally (NULL is CUDA's default stream -- what PyTorch's default stream is; use
@@ -127,6 +163,16 @@ int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
  * 4*nbatch doubles laid out as [S | Amin | Amax | nan-count-as-double].  Asynchronous on `stream`. */
 int sb200_objective_batch_device(sb200_ctx* ctx, const double* d_coeffs, int64_t nbatch,
                                  int32_t x_begin, int32_t x_end, double* d_out, void* stream);
+
+int sb200_objective_batch_device_ex(sb200_ctx* ctx, const double* d_coeffs, int64_t nbatch,
+                                    const sb200_batch_opts* opts, double* d_out, void* stream);
+
+/* Fixed-order combine of k-slab partials on the device ("one all-gather of 4 doubles per rank
+ * followed by a fixed-rank-order reduce"): d_parts[world][4][nbatch] (the gathered d_out blocks of `world`
+ * shards) -> d_out[4][nbatch]; S and nan are summed shard 0 first, Amin / Amax by min / max, a NaN in any
+ * shard's extrema poisons both.  Asynchronous on `stream`. */
+int sb200_combine_slabs_device(sb200_ctx* ctx, const double* d_parts, int32_t world, int64_t nbatch,
+                               double* d_out, void* stream);
 
 /* Dense export for ONE coefficient vector over x-planes [x_begin, x_end): writes
  * (x_end-x_begin)*n[1]*n[2] doubles (C order) to the HOST buffer `out`; also returns the grid
@@ -151,6 +197,36 @@ int sb200_export_device(sb200_ctx* ctx, const double* coeffs, int32_t what, int3
 int sb200_group_velocity(sb200_ctx* ctx, const double* coeffs, const double* h,
                          double* omega, double* vgc, double* vg, double* vph, double* k, int64_t* nan);
 
+/* ---- device groups: the batch sharded over several GPUs of ONE process ---------------------------------------
+ * Replaces the reference's mp.Pool scan (optimize.py:169-190) behind the same Python call: a group owns one
+ * context (tables, weights, stream, staging) per device; one host thread enqueues the shards on all devices
+ * before it waits for any of them.  Results do not depend on the number of devices in candidate mode (every
+ * candidate's reduction is the single-device one when the shards keep the single-device tiling, which they do
+ * for seg_size > 0; for one big batch the tiling follows the shard size and the sums agree to the last few
+ * bits); in slab mode the per-device partials are combined on the host in device order (sum / min / max / sum,
+ * NaN-poisoning), deterministically. */
+#define SB200_SHARD_AUTO        0   /* candidates when the batch is large, slabs when the grid is, else one device */
+#define SB200_SHARD_CANDIDATES  1   /* device g evaluates a contiguous block of candidates (whole segments)        */
+#define SB200_SHARD_SLABS       2   /* device g evaluates all candidates on planes g, g+G, g+2G, ... of the list    */
+#define SB200_SHARD_NONE        3   /* the first device only                                                       */
+#define SB200_SHARD_SLABS_CONTIGUOUS 4 /* slabs as contiguous x-ranges [gN/G, (g+1)N/G) (SURVEY.md 8e wording)     */
+
+typedef struct sb200_group sb200_group;
+
+/* devices: CUDA ordinals (ndevices >= 1); NULL means "all visible devices". desc->device is ignored. */
+int sb200_group_create(sb200_group** out, const sb200_grid_desc* desc, const int32_t* devices, int32_t ndevices);
+void sb200_group_destroy(sb200_group* grp);
+const char* sb200_group_last_error(const sb200_group* grp);   /* grp may be NULL: last failed create */
+int sb200_group_size(const sb200_group* grp, int32_t* ndevices);
+/* Borrow member i's context (owned by the group) for the single-device entry points (exports, streams). */
+int sb200_group_member(sb200_group* grp, int32_t i, sb200_ctx** ctx);
+int sb200_group_set_weight(sb200_group* grp, int32_t kind, const double* w, int64_t count);
+/* As sb200_objective_batch_ex (opts may be NULL), sharded as `shard` says.  used (may be NULL) receives the
+ * sharding that was applied and the number of devices that took part: used[0] = SB200_SHARD_*, used[1] = count. */
+int sb200_group_objective_batch(sb200_group* grp, const double* coeffs, int64_t nbatch, int32_t shard,
+                                const sb200_batch_opts* opts, double* S, double* Amin, double* Amax, int64_t* nan,
+                                int32_t* used);
+
 /* The context's own (non-blocking) stream as a cudaStream_t, for callers of the *_device variants. */
 int sb200_get_stream(const sb200_ctx* ctx, void** stream);
 
@@ -164,8 +240,14 @@ int sb200_last_batch_ms(const sb200_ctx* ctx, double* ms);
 int sb200_set_tiling(sb200_ctx* ctx, int32_t cand_per_thread, int32_t tile_y, int32_t tile_x);
 
 /* Register-resident DFMA throughput of `device` in TFLOP/s (2 flop per DFMA), measured with CUDA
- * events over about `seconds` of back-to-back launches.  The roofline denominator "of measured". */
+ * events over about `seconds` of back-to-back launches, best of several (chains per thread, resident warps)
+ * shapes.  The roofline denominator "of measured". */
 int sb200_fp64_peak(int32_t device, double seconds, double* tflops);
+
+/* End-to-end rate of the most recent dense export / group-velocity call of this context: bytes delivered to
+ * the caller's host buffers and the wall-clock seconds from the first launch to the last byte (chunked,
+ * double-buffered D2H through pinned staging). */
+int sb200_last_export_stats(const sb200_ctx* ctx, double* bytes, double* seconds);
 
 #ifdef __cplusplus
 }

@@ -15,11 +15,22 @@ LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "csrc", "libstenci
 SB200_W_UNIT, SB200_W_PLANE, SB200_W_DENSE = 0, 1, 2
 SB200_X_OMEGA, SB200_X_SQRTARG, SB200_X_SQRTRES = 0, 1, 2
 
+SB200_F_SCAN, SB200_F_AUTO_SCAN = 1, 2
+SHARD_AUTO, SHARD_CANDIDATES, SHARD_SLABS, SHARD_NONE, SHARD_SLABS_CONTIGUOUS = 0, 1, 2, 3, 4
+SHARD_MODES = {"auto": SHARD_AUTO, "candidates": SHARD_CANDIDATES, "slabs": SHARD_SLABS, "none": SHARD_NONE,
+               "slabs-contiguous": SHARD_SLABS_CONTIGUOUS}
+ABI_VERSION = 2
+
 EXPORTED_SYMBOLS = (
     "sb200_abi_version", "sb200_device_count", "sb200_create", "sb200_destroy", "sb200_last_error",
-    "sb200_set_weight", "sb200_objective_batch", "sb200_objective_batch_device", "sb200_export",
-    "sb200_export_device", "sb200_group_velocity", "sb200_get_stream", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling", "sb200_fp64_peak",
+    "sb200_set_weight", "sb200_objective_batch", "sb200_objective_batch_ex", "sb200_objective_batch_device",
+    "sb200_objective_batch_device_ex", "sb200_combine_slabs_device", "sb200_export", "sb200_export_device",
+    "sb200_group_velocity", "sb200_get_stream", "sb200_launch_count", "sb200_last_batch_ms", "sb200_set_tiling",
+    "sb200_fp64_peak", "sb200_last_export_stats",
+    "sb200_group_create", "sb200_group_destroy", "sb200_group_last_error", "sb200_group_size", "sb200_group_member",
+    "sb200_group_set_weight", "sb200_group_objective_batch",
 )
+_NO_STATUS = ("sb200_destroy", "sb200_last_error", "sb200_group_destroy", "sb200_group_last_error")
 
 
 class StencilB200Error(RuntimeError):
@@ -33,6 +44,11 @@ class _GridDesc(ctypes.Structure):
                 ("kcomp", ctypes.POINTER(ctypes.c_double) * 3),
                 ("Y", ctypes.c_double), ("Z", ctypes.c_double), ("Y2", ctypes.c_double), ("Z2", ctypes.c_double),
                 ("device", ctypes.c_int32)]
+
+
+class _BatchOpts(ctypes.Structure):
+    _fields_ = [("x_begin", ctypes.c_int32), ("x_stride", ctypes.c_int32), ("n_planes", ctypes.c_int32),
+                ("flags", ctypes.c_int32), ("seg_size", ctypes.c_int64)]
 
 
 _lib = None
@@ -62,6 +78,21 @@ def load_library():
     # the hot call takes plain addresses: ndarray.ctypes.data_as() costs 3 us per pointer, five of them per call
     lib.sb200_objective_batch.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
     lib.sb200_objective_batch_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp]
+    op = ctypes.POINTER(_BatchOpts)
+    lib.sb200_objective_batch_ex.argtypes = [vp, vp, ctypes.c_int64, op, vp, vp, vp, vp]
+    lib.sb200_objective_batch_device_ex.argtypes = [vp, vp, ctypes.c_int64, op, vp, vp]
+    lib.sb200_combine_slabs_device.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, vp, vp]
+    lib.sb200_last_export_stats.argtypes = [vp, dp, dp]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    lib.sb200_group_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_GridDesc), i32p, ctypes.c_int32]
+    lib.sb200_group_destroy.argtypes = [vp]
+    lib.sb200_group_destroy.restype = None
+    lib.sb200_group_last_error.argtypes = [vp]
+    lib.sb200_group_last_error.restype = ctypes.c_char_p
+    lib.sb200_group_size.argtypes = [vp, i32p]
+    lib.sb200_group_member.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(vp)]
+    lib.sb200_group_set_weight.argtypes = [vp, ctypes.c_int32, dp, ctypes.c_int64]
+    lib.sb200_group_objective_batch.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, op, vp, vp, vp, vp, i32p]
     lib.sb200_export.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, dp, dp, dp, i64p]
     lib.sb200_export_device.argtypes = [vp, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
     lib.sb200_group_velocity.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, i64p]
@@ -72,10 +103,11 @@ def load_library():
     lib.sb200_fp64_peak.argtypes = [ctypes.c_int32, ctypes.c_double, dp]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here == header and library disagree
-        if name not in ("sb200_destroy", "sb200_last_error"):
+        if name not in _NO_STATUS:
             getattr(lib, name).restype = ctypes.c_int
-    if lib.sb200_abi_version() != 1:
-        raise StencilB200Error("libstencil_b200.so has ABI version %d, expected 1" % lib.sb200_abi_version())
+    if lib.sb200_abi_version() != ABI_VERSION:
+        raise StencilB200Error("libstencil_b200.so has ABI version %d, expected %d; rebuild it "
+                               "(python -m optimize_stencil_b200._build)" % (lib.sb200_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 
@@ -108,16 +140,33 @@ def fp64_peak_tflops(device=0, seconds=0.25):
     return out.value
 
 
+def _devices_arg(devices):
+    """None -> None (single device); 'all' -> every visible device; an iterable -> a list of ordinals."""
+    if devices is None:
+        return None
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError("devices must be None, 'all' or a sequence of CUDA ordinals")
+        return list(range(max(1, device_count())))
+    devs = [int(d) for d in devices]
+    if not devs:
+        raise ValueError("devices is empty")
+    return devs
+
+
 class Context:
-    """One device-resident k-grid (sb200_ctx).  Not thread-safe; one per host thread.
+    """One device-resident k-grid: an sb200_ctx, or -- with `devices` -- an sb200_group of one sb200_ctx per GPU
+    (exports then run on the group's first device, batches are sharded over all of them).  Not thread-safe; one
+    per host thread.
 
     cos_kappa, s2, kcomp: per-axis 1-D tables exactly as the reference's init2 computes them
     (dispersion.py:268-281, 339-357) -- `dim` arrays each.
     """
 
-    def __init__(self, dim, cos_kappa, s2, kcomp, Y=1.0, Z=1.0, device=0):
+    def __init__(self, dim, cos_kappa, s2, kcomp, Y=1.0, Z=1.0, device=0, devices=None):
         self._lib = load_library()
         self._h = ctypes.c_void_p(None)
+        self._grp = ctypes.c_void_p(None)
         self.dim = int(dim)
         if self.dim not in (2, 3) or not (len(cos_kappa) == len(s2) == len(kcomp) == self.dim):
             raise ValueError("dim must be 2 or 3 with one table triple per axis")
@@ -140,17 +189,40 @@ class Context:
         dx = 1.0
         d.Y2, d.Z2 = float((Y * dx) ** 2), float((Z * dx) ** 2)
         self.shape = tuple(shape)
-        rc = self._lib.sb200_create(ctypes.byref(self._h), ctypes.byref(d))
-        if rc != 0:
-            self._h = ctypes.c_void_p(None)
-            raise StencilB200Error("sb200_create failed (%d): %s" % (rc, self._lib.sb200_last_error(None).decode()))
+        devs = _devices_arg(devices)
+        self.devices = devs if devs is not None else [int(device)]
+        self.last_shard = ("none", 1)
+        if devs is not None and len(devs) > 1:
+            arr = (ctypes.c_int32 * len(devs))(*devs)
+            rc = self._lib.sb200_group_create(ctypes.byref(self._grp), ctypes.byref(d), arr, len(devs))
+            if rc != 0:
+                self._grp = ctypes.c_void_p(None)
+                raise StencilB200Error("sb200_group_create failed (%d): %s"
+                                       % (rc, self._lib.sb200_group_last_error(None).decode()))
+            rc = self._lib.sb200_group_member(self._grp, 0, ctypes.byref(self._h))
+            if rc != 0:
+                raise StencilB200Error("sb200_group_member failed (%d)" % rc)
+        else:
+            d.device = self.devices[0]
+            rc = self._lib.sb200_create(ctypes.byref(self._h), ctypes.byref(d))
+            if rc != 0:
+                self._h = ctypes.c_void_p(None)
+                raise StencilB200Error("sb200_create failed (%d): %s" % (rc, self._lib.sb200_last_error(None).decode()))
 
     # -- plumbing -------------------------------------------------------------------------------
     def _check(self, rc, what):
         if rc != 0:
             raise StencilB200Error("%s failed (%d): %s" % (what, rc, self._lib.sb200_last_error(self._h).decode()))
 
+    def _gcheck(self, rc, what):
+        if rc != 0:
+            raise StencilB200Error("%s failed (%d): %s" % (what, rc, self._lib.sb200_group_last_error(self._grp).decode()))
+
     def close(self):
+        if getattr(self, "_grp", None) is not None and self._grp.value:
+            self._lib.sb200_group_destroy(self._grp)          # owns every member, including self._h
+            self._grp = ctypes.c_void_p(None)
+            self._h = ctypes.c_void_p(None)
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.sb200_destroy(self._h)
             self._h = ctypes.c_void_p(None)
@@ -168,8 +240,14 @@ class Context:
         self.close()
 
     # -- weights --------------------------------------------------------------------------------
+    def _set_weight(self, kind, ptr, count):
+        if self._grp.value:
+            self._gcheck(self._lib.sb200_group_set_weight(self._grp, kind, ptr, count), "sb200_group_set_weight")
+        else:
+            self._check(self._lib.sb200_set_weight(self._h, kind, ptr, count), "sb200_set_weight")
+
     def set_weight_unit(self):
-        self._check(self._lib.sb200_set_weight(self._h, SB200_W_UNIT, None, 0), "sb200_set_weight")
+        self._set_weight(SB200_W_UNIT, None, 0)
 
     def set_weight(self, w):
         """w: scalar-free array broadcastable to the grid.  Arrays that do not depend on the first
@@ -178,36 +256,82 @@ class Context:
         x_independent = w.ndim == 3 and (w.shape[0] == 1 or (w.shape[0] == self.shape[0] and w.strides[0] == 0))
         if self.dim == 3 and x_independent:
             plane = _f64(np.broadcast_to(w[:1], (1,) + self.shape[1:])[0])
-            self._check(self._lib.sb200_set_weight(self._h, SB200_W_PLANE, _dptr(plane), plane.size), "sb200_set_weight")
+            self._set_weight(SB200_W_PLANE, _dptr(plane), plane.size)
         else:
             dense = _f64(np.broadcast_to(w, self.shape))
-            self._check(self._lib.sb200_set_weight(self._h, SB200_W_DENSE, _dptr(dense), dense.size), "sb200_set_weight")
+            self._set_weight(SB200_W_DENSE, _dptr(dense), dense.size)
 
     # -- the objective --------------------------------------------------------------------------
-    def objective_batch(self, coeffs, x_begin=0, x_end=None):
-        """coeffs: (B, ncoef) full coefficient vectors -> (S, Amin, Amax, nan) arrays of length B."""
+    def _opts(self, x_begin, x_end, x_stride, seg_size, scan):
+        """sb200_batch_opts, or None for the plain whole-grid call."""
+        x_end = self.shape[0] if x_end is None else int(x_end)
+        x_begin, x_stride = int(x_begin), int(x_stride)
+        flags = SB200_F_AUTO_SCAN if scan == "auto" else (SB200_F_SCAN if scan else 0)
+        if x_begin == 0 and x_end == self.shape[0] and x_stride == 1 and not seg_size and not flags:
+            return None
+        if x_end <= x_begin:
+            raise ValueError("empty x range [%d, %d)" % (x_begin, x_end))
+        o = _BatchOpts()
+        o.x_begin, o.x_stride = x_begin, x_stride
+        o.n_planes = (x_end - x_begin + x_stride - 1) // x_stride
+        o.flags, o.seg_size = flags, int(seg_size or 0)
+        return o
+
+    def objective_batch(self, coeffs, x_begin=0, x_end=None, x_stride=1, seg_size=0, scan=False, shard="auto"):
+        """coeffs: (B, ncoef) full coefficient vectors -> (S, Amin, Amax, nan) arrays of length B.
+
+        x_begin/x_end/x_stride: the visited x-planes range(x_begin, x_end, x_stride) (k-slabs).
+        seg_size: B is a concatenation of independent segments of this many rows; every segment's results are
+                  bit-identical to a call on that segment alone.
+        scan:     True / False / 'auto': the start-grid screening kernel variant (same results).
+        shard:    with a device group: 'auto', 'candidates', 'slabs', 'slabs-contiguous' or 'none'."""
         c = _f64(coeffs)
         if c.ndim == 1:
             c = c.reshape(1, -1)
         if c.ndim != 2 or c.shape[1] != self.ncoef:
             raise ValueError("coeffs must have shape (B, %d), got %s" % (self.ncoef, c.shape))
         B = c.shape[0]
-        x_end = self.shape[0] if x_end is None else x_end
         out = np.empty((4, B))                       # S | Amin | Amax | nan (int64 in the same 8-byte slots)
         base, row = out.ctypes.data, 8 * B
-        rc = self._lib.sb200_objective_batch(self._h, c.ctypes.data, B, int(x_begin), int(x_end), base, base + row,
-                                             base + 2 * row, base + 3 * row)
-        self._check(rc, "sb200_objective_batch")
+        o = self._opts(x_begin, x_end, x_stride, seg_size, scan)
+        if self._grp.value:
+            used = (ctypes.c_int32 * 2)()
+            rc = self._lib.sb200_group_objective_batch(self._grp, c.ctypes.data, B, SHARD_MODES[shard],
+                                                       ctypes.byref(o) if o is not None else None, base, base + row,
+                                                       base + 2 * row, base + 3 * row, used)
+            self._gcheck(rc, "sb200_group_objective_batch")
+            self.last_shard = ({v: k for k, v in SHARD_MODES.items()}[used[0]], used[1])
+        elif o is None:
+            rc = self._lib.sb200_objective_batch(self._h, c.ctypes.data, B, 0, self.shape[0], base, base + row,
+                                                 base + 2 * row, base + 3 * row)
+            self._check(rc, "sb200_objective_batch")
+        else:
+            rc = self._lib.sb200_objective_batch_ex(self._h, c.ctypes.data, B, ctypes.byref(o), base, base + row,
+                                                    base + 2 * row, base + 3 * row)
+            self._check(rc, "sb200_objective_batch_ex")
         return out[0], out[1], out[2], out[3].view(np.int64)
 
-    def objective_batch_device(self, d_coeffs_ptr, nbatch, d_out_ptr, x_begin=0, x_end=None, stream=None):
+    def objective_batch_device(self, d_coeffs_ptr, nbatch, d_out_ptr, x_begin=0, x_end=None, stream=None, x_stride=1,
+                               seg_size=0, scan=False):
         """Device-pointer variant (torch tensors' .data_ptr()); asynchronous on `stream`, a raw
-        cudaStream_t value (0 / None = CUDA's default stream, i.e. torch's default stream)."""
-        x_end = self.shape[0] if x_end is None else x_end
-        rc = self._lib.sb200_objective_batch_device(self._h, ctypes.c_void_p(d_coeffs_ptr), int(nbatch), int(x_begin),
-                                                    int(x_end), ctypes.c_void_p(d_out_ptr),
-                                                    ctypes.c_void_p(stream or 0))
+        cudaStream_t value (0 / None = CUDA's default stream, i.e. torch's default stream).  Always runs on the
+        context's (first) device."""
+        o = self._opts(x_begin, x_end, x_stride, seg_size, bool(scan))
+        if o is None:
+            rc = self._lib.sb200_objective_batch_device(self._h, ctypes.c_void_p(d_coeffs_ptr), int(nbatch), 0,
+                                                        self.shape[0], ctypes.c_void_p(d_out_ptr),
+                                                        ctypes.c_void_p(stream or 0))
+        else:
+            rc = self._lib.sb200_objective_batch_device_ex(self._h, ctypes.c_void_p(d_coeffs_ptr), int(nbatch),
+                                                           ctypes.byref(o), ctypes.c_void_p(d_out_ptr),
+                                                           ctypes.c_void_p(stream or 0))
         self._check(rc, "sb200_objective_batch_device")
+
+    def combine_slabs_device(self, d_parts_ptr, world, nbatch, d_out_ptr, stream=None):
+        """[world][4][nbatch] gathered slab partials -> [4][nbatch], fixed shard order, on the device."""
+        rc = self._lib.sb200_combine_slabs_device(self._h, ctypes.c_void_p(d_parts_ptr), int(world), int(nbatch),
+                                                  ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream or 0))
+        self._check(rc, "sb200_combine_slabs_device")
 
     def export(self, coeffs, what=SB200_X_OMEGA, x_begin=0, x_end=None):
         """Dense omega / sqrtarg / sqrtres for one coefficient vector -> (array, Amin, Amax, nan)."""
@@ -256,14 +380,35 @@ class Context:
         self._check(self._lib.sb200_get_stream(self._h, ctypes.byref(st)), "sb200_get_stream")
         return st.value or 0
 
+    def _members(self):
+        if not self._grp.value:
+            return [self._h]
+        out = []
+        for i in range(len(self.devices)):
+            h = ctypes.c_void_p(None)
+            self._gcheck(self._lib.sb200_group_member(self._grp, i, ctypes.byref(h)), "sb200_group_member")
+            out.append(h)
+        return out
+
     @property
     def launch_count(self):
-        n = ctypes.c_int64(0)
-        self._check(self._lib.sb200_launch_count(self._h, ctypes.byref(n)), "sb200_launch_count")
-        return n.value
+        """Kernels launched so far (summed over the devices of a group)."""
+        total = 0
+        for h in self._members():
+            n = ctypes.c_int64(0)
+            self._check(self._lib.sb200_launch_count(h, ctypes.byref(n)), "sb200_launch_count")
+            total += n.value
+        return total
 
     @property
     def last_batch_ms(self):
         ms = ctypes.c_double(0.0)
         self._check(self._lib.sb200_last_batch_ms(self._h, ctypes.byref(ms)), "sb200_last_batch_ms")
         return ms.value
+
+    @property
+    def last_export_stats(self):
+        """(bytes delivered to host buffers, wall seconds) of the most recent export / group_velocity call."""
+        b, t = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        self._check(self._lib.sb200_last_export_stats(self._h, ctypes.byref(b), ctypes.byref(t)), "sb200_last_export_stats")
+        return b.value, t.value

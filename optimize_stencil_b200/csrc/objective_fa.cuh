@@ -74,7 +74,14 @@ struct RowLayoutFA {
 };
 
 // Shared memory: Cand[C] | rows | s_red | s_redu | s_umax | s_smax
-template <int C, bool UNIT, int WK>
+//
+// SCAN: the variant for start-grid screening (Optimize's first pass over the whole start grid, optimize.py:118-134
+// of the reference, where most candidates violate the CFL limit at most k-points).  A warp whose 32 lanes x J chains
+// all have v >= 1 + 2^-12 -- s > 1, omega is NaN whatever the last bits of sqrtarg are -- skips the evaluation and
+// takes NaN directly; the extrema were already dealt with by then.  Results are bit-identical to the plain variant;
+// it is a separate instantiation because the extra merge point costs the plain MID loop two register moves per
+// iteration (measured: 682 -> 672 G evals/s on the 4096 x 512^3 batch).
+template <int C, bool UNIT, int WK, bool SCAN>
 __global__ void __launch_bounds__(SB200_MAXTHREADS, (C <= 4 ? SB200_MINBLOCKS_C4 : SB200_MINBLOCKS_C8))
 objective_kernel_fa(const GridDev g, const BatchArgs a) {
     constexpr int ROW = RowLayoutFA<C>::ROW;
@@ -96,17 +103,18 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     const int lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x / a.n_ztiles;
     const int ztile = blockIdx.x - chunk * a.n_ztiles;
-    const int xs = a.x_begin + blockIdx.y * a.tile_x;
-    const int xe = min(xs + a.tile_x, a.x_end);
+    const int is = blockIdx.y * a.tile_x;                 // plane indices [is, ie) of the visited plane list
+    const int ie = min(is + a.tile_x, a.n_planes);
     const int ys = blockIdx.z * a.tile_y;
-    const long long b0 = (long long)chunk * C;
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
 
     if (tid == 0) s_force = 0;
     __syncthreads();
     if (tid < C) {
-        long long b = b0 + tid;
-        if (b >= a.B) b = a.B - 1;  // pad the last chunk with a copy; its results are not written
+        const int seg = chunk / a.chunks_per_seg;
+        const long long bend = (long long)(seg + 1) * a.seg_size;
+        long long b = (long long)seg * a.seg_size + (long long)(chunk - seg * a.chunks_per_seg) * C + tid;
+        if (b >= bend) b = bend - 1;  // pad the segment's last chunk with a copy; its results are not written
         Cand& c = cand[tid];
         load_candidate(c, a.coeffs + b * a.ncoef, a.ncoef);
         // Are the guards of the header sufficient for this candidate?  (every test is false for NaNs)
@@ -119,7 +127,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         // maximum sits on the far corner for Yee-like stencils, on an axis end for smoothed ones like Lehe's)
         double probe = 0.;
         for (int q = 1; q < 8; ++q) {
-            const int xc = (q & 1) ? a.x_end - 1 : a.x_begin, yc = (q & 2) ? g.ny - 1 : 0, zc = (q & 4) ? g.nz - 1 : 0;
+            const int xc = (q & 1) ? a.x_begin + (a.n_planes - 1) * a.x_stride : a.x_begin, yc = (q & 2) ? g.ny - 1 : 0, zc = (q & 4) ? g.nz - 1 : 0;
             probe = fmax(probe, sqrtarg_exact_at<UNIT>(&c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc],
                                                        g.sz2[zc], g.Y2, g.rY2, g.Z2, g.rZ2));
         }
@@ -141,11 +149,12 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     }
 
     double* wrows = s_rows + (size_t)warp * ROWS * ROW;   // this warp's private table
-    for (int x = xe - 1; x >= xs; --x) {
+    for (int i = ie - 1; i >= is; --i) {
+        const int x = a.x_begin + i * a.x_stride;
         // Load balance: the cost of a k-point depends on its class, i.e. on |k|, i.e. on z.  Warp w
-        // therefore takes z slice (w + x) mod nwarps of the CTA's z tile for plane x, so that over an
+        // therefore takes z slice (w + i) mod nwarps of the CTA's z tile for plane i, so that over an
         // x range every warp sees every z slice and all warps of the CTA finish together.
-        const int zslice = (warp + (x - a.x_begin)) % nwarps;
+        const int zslice = (warp + i) % nwarps;
         const int zraw = ztile * blockDim.x + zslice * 32 + lane;
         // Lanes past the end of the z axis repeat its last point: all 32 lanes stay converged (votes with
         // a constant full mask), the extrema are unaffected and their sums are simply not accumulated.
@@ -278,6 +287,21 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
                 } else {
+                    if (SCAN) {
+                        // v >= 1 + 2^-12 as a signed compare of high words.  +inf and a positive NaN pass as well: omega
+                        // is NaN for those too, and a positive NaN was already caught by the maximum filter above (its
+                        // high word exceeds every threshold), i.e. the iteration was redone and the extrema are poisoned;
+                        // a sign-bit NaN fails the test and goes on to the guards below.
+                        bool beyond = true;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) beyond = beyond && (__double2hiint(v[j]) >= 0x3ff00100);
+                        if (__all_sync(FULL, beyond)) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                if (active) S[c] = __longlong_as_double(0x7ff8000000000000ll);   // NaN is sticky in the sum
+                            continue;
+                        }
+                    }
                     double z2[J];
 #pragma unroll
                     for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);             // dt^2 A
@@ -329,7 +353,10 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     int bx = blockIdx.x;                                   // re-derived from an opaque copy: chunk / ztile / b0 need not stay alive
     asm volatile("" : "+r"(bx));
     const int chunk_e = bx / a.n_ztiles;
-    finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk_e, bx - chunk_e * a.n_ztiles, (long long)chunk_e * C);
+    const int seg_e = chunk_e / a.chunks_per_seg;
+    const long long b0_e = (long long)seg_e * a.seg_size + (long long)(chunk_e - seg_e * a.chunks_per_seg) * C;
+    finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk_e, bx - chunk_e * a.n_ztiles, b0_e,
+                         (long long)(seg_e + 1) * a.seg_size);
 }
 
 }  // namespace sb200

@@ -20,8 +20,20 @@ Additions that do not exist in the reference:
     dispersion.py:94-96) plus speculative evaluation of the n forward-difference neighbours SciPy's
     SLSQP is about to request (same absolute step 1.4901161193847656e-08), so that the objective, both
     constraints and all their finite-difference Jacobians at one iterate cost ONE launch;
-  * `k` (dense) is built lazily -- the device recomputes k per point and never needs it.
+  * `k` (dense) is built lazily -- the device recomputes k per point and never needs it;
+  * `devices`: batches large enough to pay for it are sharded over several GPUs of this process by the
+    library's device group (sb200_group_*), replacing the reference's mp.Pool scan (optimize.py:169-190);
+  * `view()`: a cheap per-search facade sharing the tables and the device context, with its own result
+    cache -- what lets `Optimize` run many SLSQP searches in lock-step, one launch per round.
+
+Determinism: every result a search sees comes from a launch (or launch SEGMENT) made of exactly the points
+that search asked for -- an iterate and its forward-difference neighbours -- and a finite difference never
+mixes two launches (cache entries carry their launch id).  The library guarantees that a segment's results do
+not depend on what else shares the launch, so a search is bit-identical whether it runs alone or next to
+thousands of others.
 """
+import os
+
 import numpy as np
 import scipy.interpolate as spinterp
 
@@ -48,7 +60,12 @@ class Dispersion:
     dim = 0
     dt_multiplier = 1.0
     stencil = None
-    device = 0                 # CUDA ordinal used when the context is (re)created
+    device = None              # CUDA ordinal of a single-device context (None: $OPTSTENCIL_DEVICE, else 0)
+    devices = None             # None: automatic (one device; every visible device once a batch is large enough to
+                               # pay for the extra contexts, or what $OPTSTENCIL_DEVICES says: "all", "0,1,..."),
+                               # 'all', or a sequence of CUDA ordinals
+    auto_multi_evals = float(2 ** 36)   # k-point x candidate evaluations in ONE batch from which `devices = None`
+                                        # brings up the other GPUs (~0.1 s of one B200; a context costs ~0.3 s once)
     fd_prefetch = True         # evaluate x + h*e_i alongside every cache miss (see module docstring)
     cache_size = 4096
 
@@ -61,6 +78,9 @@ class Dispersion:
         self._cache = {}
         self._fd_last = None
         self._fd_index = {}
+        self._launch_id = 0
+        self._submit = None        # views only: hands a block of coefficient rows to the lock-step server
+        self._parent = None        # views only
         self._k = None
         self.init2_run = False
         self.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
@@ -103,7 +123,27 @@ class Dispersion:
         state['_w_dirty'] = True
         state['_cache'] = {}
         state['_fd_last'] = None
+        state['_submit'] = None
+        state['_parent'] = None
         return state
+
+    # -- per-search views (new) -------------------------------------------------------------------
+    def view(self, submit=None):
+        """A facade for ONE search: same tables, stencil, weight and device context as this object, but its own
+        parameters, result cache and finite-difference memo.  `submit(C) -> (S, Amin, Amax, nan)` replaces the
+        direct launch (the lock-step server of optimize.py passes its own); None launches directly."""
+        self._context()                      # tables, context and weight upload happen once, on the parent
+        v = object.__new__(type(self))
+        v.__dict__.update(self.__dict__)
+        v._parameters = None
+        v._coefficients = None
+        v._cache = {}
+        v._fd_last = None
+        v._launch_id = 0
+        v._submit = submit
+        v._parent = self
+        v.stats = dict(launches=0, evaluated=0, hits=0, misses=0)
+        return v
 
     # -- weight function ------------------------------------------------------------------------
     @property
@@ -124,12 +164,39 @@ class Dispersion:
         self._fd_last = None
 
     # -- device context ---------------------------------------------------------------------------
-    def _context(self):
+    def _wanted_devices(self, evals):
+        """CUDA ordinals the context should span for a batch of `evals` evaluations."""
+        devs = self.devices
+        if devs is None:
+            devs = os.environ.get('OPTSTENCIL_DEVICES') or None
+            if devs is not None and devs != 'all':
+                devs = [int(t) for t in devs.split(',') if t.strip() != '']
+        if devs is None:
+            first = self.device if self.device is not None else int(os.environ.get('OPTSTENCIL_DEVICE', 0))
+            if evals >= self.auto_multi_evals and _capi.device_count() > 1:
+                n = _capi.device_count()
+                return [(first + i) % n for i in range(n)]
+            return [first]
+        if isinstance(devs, str):
+            return list(range(max(1, _capi.device_count())))
+        return [int(d) for d in devs]
+
+    def _context(self, evals=0.0):
+        """The device context (created lazily; grown to a multi-GPU group when a batch is large enough)."""
+        if self._parent is not None:
+            return self._parent._context(evals)
         if not self.init2_run:
             self.init2()
+        if self._ctx is not None and evals >= self.auto_multi_evals and self.devices is None:
+            want = self._wanted_devices(evals)
+            if len(want) > len(self._ctx.devices):
+                self._ctx.close()            # never shrinks back: the extra contexts are paid for once
+                self._ctx = None
         if self._ctx is None:
             cos, s2, kc = self._tables
-            self._ctx = _capi.Context(self.dim, cos, s2, kc, Y=self.Y, Z=self.Z, device=self.device)
+            want = self._wanted_devices(evals)
+            self._ctx = _capi.Context(self.dim, cos, s2, kc, Y=self.Y, Z=self.Z, device=want[0],
+                                      devices=want if len(want) > 1 else None)
             self._w_dirty = True
         if self._w_dirty:
             w = self._w
@@ -168,20 +235,31 @@ class Dispersion:
     # cache entry: [S, Amin, Amax, nan, full coefficient row, gate]; gate = (dt_multiplier, stencil_ok,
     # dt_ok, usable) is filled on first use, because its ValueErrors must surface only for points a
     # caller actually asked about (prefetched finite-difference neighbours may be garbage).
+    def _grid_points(self):
+        return float(self.N) ** self.dim
+
+    def _launch(self, C, **kw):
+        """One launch for the coefficient rows C -> (S, Amin, Amax, nan).  A view hands the rows to its server
+        instead (they then travel as one SEGMENT of a shared launch: same bits as the direct call)."""
+        if self._submit is not None:
+            return self._submit(C)
+        return self._context(len(C) * self._grid_points()).objective_batch(C, **kw)
+
     def _raw_batch(self, P):
         """(B, dof) parameters -> (S, Amin, Amax, nan, C) via ONE launch; fills the cache."""
-        ctx = self._context()
         C = self.stencil.coefficients_batch(P)
-        S, Amin, Amax, nan = ctx.objective_batch(C)
+        S, Amin, Amax, nan = self._launch(C)
         self.stats['launches'] += 1
         self.stats['evaluated'] += len(P)
+        self._launch_id += 1
+        lid = self._launch_id
         cache = self._cache
         if len(cache) + len(P) > self.cache_size:
             for key in list(cache)[:len(cache) // 2 + len(P)]:   # drop the oldest half
                 del cache[key]
         Sl, lo, hi, nl = S.tolist(), Amin.tolist(), Amax.tolist(), nan.tolist()
         for i in range(len(P)):
-            cache[P[i].tobytes()] = [Sl[i], lo[i], hi[i], nl[i], C[i], None]
+            cache[P[i].tobytes()] = [Sl[i], lo[i], hi[i], nl[i], C[i], None, lid]
         return S, Amin, Amax, nan, C
 
     def _entry(self, parameters):
@@ -212,9 +290,6 @@ class Dispersion:
         self._raw_batch(P)
         return self._cache[key]
 
-    def _raw(self, parameters):
-        return self._entry(parameters)
-
     def _gate(self, e):
         """(stencil_ok, dt_ok, usable) of a cache entry -- dispersion.py:284-307 / 360-385, 129-154."""
         g = e[5]
@@ -222,9 +297,9 @@ class Dispersion:
             return g[1], g[2], g[3]
         S, Amin, Amax, nan, c = e[0], e[1], e[2], e[3], e[4]
         if not Amin < 0:                     # also taken when Amin is NaN, as `not a < 0` is
-            sok = self._corner_min(c)
+            sok = self._corner_min(c)        # min(b): a shape-(1,) array in the reference
         else:
-            sok = Amin
+            sok = Amin                       # a = np.min(sqrtarg): a NumPy scalar in the reference
         if sok != sok:
             raise ValueError("stencil_ok got NaN")
         if sok < 0:
@@ -252,11 +327,13 @@ class Dispersion:
         if not np.any(ok):
             return out
         Pok = np.ascontiguousarray(P[ok])
-        if len(Pok) * 4 <= self.cache_size:
+        if len(Pok) * 4 <= self.cache_size and self._submit is None:
             S, Amin, Amax, nan, C = self._raw_batch(Pok)
         else:
             C = self.stencil.coefficients_batch(Pok)
-            S, Amin, Amax, nan = self._context().objective_batch(C)
+            # large batches are what a start-grid screening looks like: let the library pick the kernel variant
+            # with the all-NaN shortcut when most rows violate the CFL limit (same results either way)
+            S, Amin, Amax, nan = self._launch(C, scan='auto') if self._submit is None else self._launch(C)
             self.stats['launches'] += 1
             self.stats['evaluated'] += len(Pok)
         with np.errstate(divide='ignore', invalid='ignore'):
@@ -285,18 +362,25 @@ class Dispersion:
 
     # -- the reference's scalar API ----------------------------------------------------------------
     def stencil_ok(self, parameters):
+        """min(sqrtarg) when that is negative (a NumPy scalar, as np.min gives), else the smallest corner value
+        (a shape-(1,) array, as min() over the record fields gives) -- dispersion.py:284-307, 360-385."""
         self.parameters = parameters
         e = self._entry(parameters)
         if e is None:
             return -1
-        return np.array([self._gate(e)[0]])
+        sok = self._gate(e)[0]
+        return np.float64(sok) if e[1] < 0 else np.array([sok])
 
     def dt_ok(self, parameters):
+        """CFL margin; a negative stencil_ok is passed through unchanged (dispersion.py:129-154)."""
         self.parameters = parameters
         e = self._entry(parameters)
         if e is None:
             return -1.
-        return np.array([self._gate(e)[1]])
+        sok, dtok, _ = self._gate(e)
+        if sok < 0:
+            return np.float64(sok) if e[1] < 0 else np.array([sok])
+        return np.array([dtok])
 
     def omega(self, parameters):
         """omega(k) on the dense grid, or None when the constraints are violated (dispersion.py:164-196)."""
@@ -359,16 +443,22 @@ class Dispersion:
         if not np.all(dx) or not np.all(np.isfinite(p)):
             self._fd_last = (key, p, None, None, self._cache)
             return p, None, None
-        entries = [self._entry(p)]                           # a miss evaluates all n + 1 points at once
-        P = np.repeat(p[None, :], n, axis=0)
-        P[np.arange(n), np.arange(n)] = ph                   # row i: copy(x); x1[i] = x[i] + h
-        if not self.fd_prefetch:
-            missing = [i for i in range(n) if P[i].tobytes() not in self._cache]
-            if missing:
-                self._raw_batch(np.ascontiguousarray(P[missing]))
-        entries += [self._entry(P[i]) for i in range(n)]
+        P = np.repeat(p[None, :], n + 1, axis=0)
+        P[np.arange(1, n + 1), np.arange(n)] = ph            # row 0: x; row i + 1: copy(x); x1[i] = x[i] + h
+        cache = self._cache
+        entries = [cache.get(P[i].tobytes()) for i in range(n + 1)]
+        lid = entries[0][6] if entries[0] is not None else None
+        if lid is None or any(e is None or e[6] != lid for e in entries):
+            # x and its n neighbours in ONE launch: a forward difference never mixes the sums of two launches
+            # (they may differ in their last bits), and a point cached without its neighbours -- a start taken
+            # from a screening batch, prefetch switched off -- costs one launch, not one per neighbour
+            self.stats['misses'] += 1
+            self._raw_batch(P)
+            entries = [cache[P[i].tobytes()] for i in range(n + 1)]
+        else:
+            self.stats['hits'] += n + 1
         self._fd_last = (key, p, dx.tolist(), entries, self._cache)
-        self._fd_last_point = P[n - 1]
+        self._fd_last_point = P[n]
         return p, self._fd_last[2], entries
 
     def _fd_jac(self, value_of, scalar_fun, x):

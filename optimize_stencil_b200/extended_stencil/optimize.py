@@ -5,27 +5,30 @@ constraints and options, optimize.py:136,142).  What changes is the data-paralle
 
   reference: mp.Pool(nproc).imap(_optimize_single, starts) -- one whole SLSQP run per CPU worker,
              every objective / constraint call a fresh ~25-pass NumPy sweep (optimize.py:169-190);
-  here:      the searches run in this process against the GPU-backed Dispersion objects.  The start
-             grid is screened in TWO batched launches (CFL time step of every start, then
-             feasibility of every start), and inside each search one launch serves the objective,
-             both constraints and all their finite-difference points of an iterate (see
-             dispersion.py).  `--singlecore` is accepted and changes nothing by default.
+  here:      1. the start grid is screened in ONE batched launch (stencil_ok and the CFL time step of every
+                start; optimize.py:118-134), infeasible starts never reach SciPy;
+             2. the surviving searches run CONCURRENTLY in this process, one thread each, in lock-step: when
+                every live search has asked for its next iterate (the iterate and its finite-difference
+                neighbours), ONE launch serves them all -- each search's points travel as one segment of that
+                launch, and the library guarantees a segment's results are bit-identical to a launch of its
+                own (include/stencil_b200.h, sb200_objective_batch_ex), so every search is bit-identical to
+                its stand-alone run (`lockstep = False`) whatever shares the launch;
+             3. a large start grid is additionally split over worker PROCESSES (`workers`), one GPU per
+                worker round-robin over the visible devices, which spreads SciPy's own per-iteration
+                Python time over the host cores; each worker runs step 2 on its share.  Starts are
+                independent and deterministic, so the result does not depend on the number of workers,
+                threads or GPUs.
              SLSQP is handed the forward differences it would take itself as `jac` callables and the
              constraint list stacked into one vector-valued constraint (`exact_fd_jac`: same points, same
              arithmetic, same rows -- the search is bit-identical, the Python overhead per iterate drops 3x).
-             What remains is SciPy's own per-iteration Python time.  It can be spread over worker processes
-             that share the GPU (`args.workers = N` or the environment variable OPTSTENCIL_WORKERS=N; every
-             worker re-creates its device context lazily, exactly like the reference's pickled Dispersion
-             objects re-run init2; each start is independent and deterministic, so the result does not depend
-             on the number of workers) -- but measured on one B200 without MPS this does not pay: the
-             workers' small launches time-slice the device (4096 starts on 128^3: 29.7 s in-process, 31.5 s
-             with 8 workers, tools/workers_timing.py), so it stays opt-in.
+             `--singlecore` keeps everything in this process (no worker processes), like the reference.
 
 The printed lines keep the reference's format (optimize.py:71, 144, 191, 200-202).
 """
 import itertools
 import os
 import sys
+import threading
 
 import numpy as np
 import scipy.optimize as scop
@@ -122,12 +125,154 @@ class _stacked_constraints:
 SLSQP_OPTIONS = dict(disp=False, iprint=2)
 
 
+class _Request:
+    __slots__ = ("parent", "C", "result", "error", "lock")
+
+    def __init__(self, parent, C):
+        self.parent, self.C, self.result, self.error = parent, C, None, None
+        self.lock = threading.Lock()
+        self.lock.acquire()                      # released when it is this request's turn to continue
+
+
+class _LockStep:
+    """Runs many independent searches as cooperatively scheduled threads and merges their device work into rounds.
+
+    Exactly ONE search thread runs at any time (a baton is passed explicitly), so the threads never fight over
+    the interpreter lock -- with dozens of runnable threads CPython's forced GIL hand-overs cost more than the
+    searches themselves.  A search that needs the objective queues its coefficient rows (`submit`) and passes the
+    baton to the next search whose results are ready; when none is -- every live search waits for results -- the
+    thread holding the baton runs the round: the queued blocks are concatenated per (dispersion object, block
+    length) and evaluated with ONE segmented launch each; every block is one segment, i.e. bit-identical to a
+    launch of its own.  What the rounds remove is the per-iterate launch + sync latency (~45 us each) and the GPU
+    idling between the small launches of a sequential scan; SciPy's own Python time is unchanged."""
+
+    pin = os.environ.get('OPTSTENCIL_PIN', '1') != '0'
+
+    def __init__(self, pin_index=-1):
+        self.pin_index = pin_index   # which of the allowed cores the search threads share (-1: the last one)
+        self._waiting = []           # requests queued for the next round
+        self._ready = []             # requests whose results are in (or start tokens), in wake-up order
+        self._idle = threading.Lock()
+        self.rounds = 0
+        self.launches = 0
+        self.rows = 0
+
+    def submitter(self, parent):
+        def submit(C):
+            req = _Request(parent, C)
+            self._waiting.append(req)
+            self._pass_baton()
+            req.lock.acquire()                   # immediately, if this thread ran the round and is first in line
+            if req.error is not None:
+                raise req.error
+            return req.result
+        return submit
+
+    def _pass_baton(self):
+        """Called by the running thread just before it blocks or exits."""
+        if not self._ready and self._waiting:
+            self._round()
+        if self._ready:
+            self._ready.pop().lock.release()
+        else:
+            self._idle.release()                 # nothing ready, nothing waiting: every thread is done
+
+    def _round(self):
+        batch, self._waiting = self._waiting, []
+        try:
+            groups = {}
+            for req in batch:
+                groups.setdefault((id(req.parent), len(req.C)), []).append(req)
+            for reqs in groups.values():
+                parent, seg = reqs[0].parent, len(reqs[0].C)
+                C = np.concatenate([r.C for r in reqs]) if len(reqs) > 1 else reqs[0].C
+                ctx = parent._context(len(C) * parent._grid_points())
+                S, Amin, Amax, nan = ctx.objective_batch(C, seg_size=seg if len(reqs) > 1 else 0)
+                self.launches += 1
+                self.rows += len(C)
+                for n, r in enumerate(reqs):
+                    sl = slice(n * seg, (n + 1) * seg)
+                    r.result = (S[sl], Amin[sl], Amax[sl], nan[sl])
+            self.rounds += 1
+        except BaseException as exc:             # a failed launch fails every search that waited for it
+            for r in batch:
+                if r.result is None:
+                    r.error = exc
+        batch.reverse()                          # popped from the end: first come, first served
+        self._ready = batch
+
+    def run(self, jobs, nthreads):
+        """jobs: callables; returns their results in order (the first exception of any job is re-raised)."""
+        results = [None] * len(jobs)
+        errors = []
+        nxt = [0]
+        nthreads = max(1, min(nthreads, len(jobs)))
+        tokens = [_Request(None, None) for _ in range(nthreads)]
+
+        def worker(token):
+            if core is not None:
+                try:
+                    os.sched_setaffinity(0, {core})      # 0 = the calling thread
+                except OSError:
+                    pass
+            token.lock.acquire()                 # wait for the baton
+            try:
+                while not errors:
+                    n = nxt[0]
+                    nxt[0] += 1
+                    if n >= len(jobs):
+                        break
+                    try:
+                        results[n] = jobs[n]()
+                    except BaseException as exc:
+                        errors.append(exc)
+            finally:
+                self._pass_baton()
+
+        # Only one search thread runs at a time, so they all share ONE core: a baton hand-over is then a same-core
+        # context switch with warm caches (~5 us) instead of waking an idle core (100-300 us measured).
+        core = None
+        if self.pin and hasattr(os, 'sched_setaffinity'):
+            allowed = sorted(os.sched_getaffinity(0))
+            core = allowed[self.pin_index % len(allowed)] if allowed else None
+        self._idle.acquire()
+        threads = [threading.Thread(target=worker, args=(tok,), daemon=True) for tok in tokens]
+        for t in threads:
+            t.start()
+        self._ready = tokens[::-1]
+        self._ready.pop().lock.release()         # the first baton
+        self._idle.acquire()                     # released by the last thread to finish
+        self._idle.release()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+
+def _worker_scan(task):
+    """Entry point of a worker process: one share of the start grid, on one GPU."""
+    opt, indices, starts, screen, device, rank = task
+    for d in (opt.dispersion, opt.dispersion_high):
+        d.device = device
+        d.devices = [device]
+    return indices, opt._scan_local(starts, screen, pin_index=rank)
+
+
 class Optimize:
     """Holds the low- and high-resolution dispersion objects and runs the start-grid scan."""
 
     # Hand SciPy the finite differences it would take anyway (same points, same arithmetic, from the
     # result cache).  The search is bit-identical either way; OPTSTENCIL_FD_JAC=0 lets SciPy do them.
     exact_fd_jac = os.environ.get('OPTSTENCIL_FD_JAC', '1') != '0'
+    # Run the searches of a scan concurrently, one launch per round (bit-identical to running them one by one).
+    lockstep = os.environ.get('OPTSTENCIL_LOCKSTEP', '1') != '0'
+    lockstep_threads = int(os.environ.get('OPTSTENCIL_THREADS', 256))
+    # Worker processes for large start grids: None = automatic (none below `workers_min_starts` searches, else one
+    # per `starts_per_worker` searches up to the physical cores), 0 = never, N = exactly N.
+    workers = None
+    workers_min_starts = 512
+    starts_per_worker = 128
 
     def __init__(self, args):
         self.args = args
@@ -152,6 +297,7 @@ class Optimize:
         self.dtmin, self.dtmax = self.args.dtrange[0], self.args.dtrange[1]
         self.constraints = self._constraint_list(self.dispersion)
         self.constraints_high = self._constraint_list(self.dispersion_high)
+        self.scan_stats = {}
 
     def _constraint_list(self, dispersion):
         cons = [dict(type='ineq', fun=dispersion.stencil_ok), dict(type='ineq', fun=dispersion.dt_ok)]
@@ -178,19 +324,27 @@ class Optimize:
                              options=dict(SLSQP_OPTIONS))
 
     # -- one start (optimize.py:115-139) ----------------------------------------------------------
-    def _optimize_single(self, x0):
+    def _optimize_single(self, x0, low=None, high=None, screened=None):
+        """One search.  `low` / `high`: the dispersion objects (or per-search views of them) to run it on;
+        `screened`: (dt_ok at dt = 0, stencil_ok) of this start from the batched screening, else they are
+        evaluated here like the reference does."""
+        low = self.dispersion if low is None else low
+        high = self.dispersion_high if high is None else high
         x0 = list(x0)
         if x0[0] is None:
             x0[0] = 0
-            dt_ok = np.asarray(self.dispersion.dt_ok(x0)).item()
+            dt_ok = np.asarray(low.dt_ok(x0)).item() if screened is None else float(screened[0])
             if dt_ok < 0:
                 return x0, None, float('inf')
             x0[0] = max(min(dt_ok, self.dtmax), self.dtmin)
         x0 = np.asarray(x0, dtype=float)
-        if self.dispersion.stencil_ok(x0) < 0:
+        # sqrtarg does not depend on dt, so the screening's stencil_ok (taken at dt = 0 when dt follows the CFL
+        # rule) is the value the reference computes here
+        if (low.stencil_ok(x0) if screened is None else screened[1]) < 0:
             return x0, None, float('inf')
-        res = self._minimize(self.dispersion, self.constraints, x0)
-        return x0, res, self.dispersion_high.norm(res.x)
+        cons = self.constraints if low is self.dispersion else self._constraint_list(low)
+        res = self._minimize(low, cons, x0)
+        return x0, res, high.norm(res.x)
 
     def _optimize_final(self, x0):
         res = self._minimize(self.dispersion_high, self.constraints_high, x0)
@@ -209,45 +363,101 @@ class Optimize:
         return list(itertools.product(dts, *axes))
 
     def _prescreen(self, starts):
-        """Warm the result cache for the whole start grid with batched launches (replaces the per-start
-        NumPy sweeps the pool workers did first: optimize.py:118-134)."""
-        rows = [[0.0 if v is None else v for v in s] for s in starts]
-        if not rows:
-            return
-        P = np.asarray(rows, dtype=float)
-        first = self.dispersion.evaluate_batch(P)
-        if starts[0][0] is None:   # dt comes from the CFL limit at dt = 0, clipped to dtrange
-            ok = first['dt_ok'] >= 0
-            P = P[ok]
-            P[:, 0] = np.clip(first['dt_ok'][ok], self.dtmin, self.dtmax)
-            if len(P):
-                self.dispersion.evaluate_batch(P)
+        """stencil_ok and dt_ok of every start from ONE batched launch (replaces the per-start NumPy sweeps the
+        pool workers did first: optimize.py:118-134).  Rows whose dt follows the CFL rule are evaluated at
+        dt = 0, as the reference does; both constraints derive from the bit-exact grid extrema, so they are
+        the values the scalar API returns.  -> array [n_starts, 2] = (dt_ok, stencil_ok)."""
+        if not starts:
+            return np.empty((0, 2))
+        P = np.asarray([[0.0 if v is None else v for v in s] for s in starts], dtype=float)
+        out = self.dispersion.evaluate_batch(P)
+        return np.stack([out['dt_ok'], out['stencil_ok']], axis=1)
 
-    def optimize(self):
-        """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
-        starts = self.start_grid()
-        workers = int(getattr(self.args, 'workers', 0) or os.environ.get('OPTSTENCIL_WORKERS', 0) or 0)
-        pool = None
+    def _scan_local(self, starts, screen, pin_index=-1):
+        """Run the searches of `starts` in this process -> list of (x0, res, norm) in order."""
+        low, high = self.dispersion, self.dispersion_high
+        lockstep = self.lockstep and len(starts) >= 2
+        server = _LockStep(pin_index) if lockstep else None
+        sub_low = server.submitter(low) if lockstep else None
+        sub_high = sub_low if high is low else (server.submitter(high) if lockstep else None)
+        low._context(), high._context()                        # contexts and weights before any thread starts
+
+        def job(s, sc):
+            def run():
+                vl = low.view(sub_low)
+                if high is low:
+                    vh = vl
+                else:
+                    vh = high.view(sub_high)
+                    vh.fd_prefetch = False                     # the high-resolution object only scores the result
+                return self._optimize_single(s, vl, vh, sc), vl.stats, (None if vh is vl else vh.stats)
+            return run
+
+        jobs = [job(s, sc) for s, sc in zip(starts, screen)]
+        done = server.run(jobs, self.lockstep_threads) if lockstep else [j() for j in jobs]
+        for _, sl, sh in done:                                 # the views' counters end up on the shared objects
+            for d, st in ((low, sl), (high, sh)):
+                if st is not None:
+                    for key, v in st.items():
+                        d.stats[key] += v
+        if lockstep:
+            self.scan_stats = dict(rounds=server.rounds, launches=server.launches, rows=server.rows)
+        return [r for r, _, _ in done]
+
+    def _worker_count(self, nstarts):
+        w = getattr(self.args, 'workers', None)
+        if w is None:
+            w = os.environ.get('OPTSTENCIL_WORKERS')
+        if w is None:
+            w = self.workers
+        if getattr(self.args, 'singlecore', False) and w is None:
+            return 0
+        if w is None:
+            if nstarts < self.workers_min_starts:
+                return 0
+            try:
+                import psutil
+                cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+            except ImportError:
+                cores = os.cpu_count() or 1
+            w = min(cores, max(1, nstarts // self.starts_per_worker))
+        w = int(w)
+        return w if w > 1 and nstarts >= 2 * w else 0
+
+    def _scan(self, starts, screen):
+        workers = self._worker_count(len(starts))
         method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')       # never fork a live CUDA context
         if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
             workers = 0
-        if workers > 1 and len(starts) >= 2 * workers and not getattr(self.args, 'singlecore', False):
-            import multiprocessing as mp
-            pool = mp.get_context(method).Pool(workers)
-            results = pool.imap(self._optimize_single, starts, chunksize=max(1, len(starts) // (8 * workers)))
-        else:
-            self._prescreen(starts)
-            results = map(self._optimize_single, starts)
+        if workers <= 1:
+            return self._scan_local(starts, screen)
+        import multiprocessing as mp
+        from .. import _capi
+        ndev = max(1, _capi.device_count()) if method == 'spawn' else 1
+        first = self.dispersion.device if self.dispersion.device is not None else int(os.environ.get('OPTSTENCIL_DEVICE', 0))
+        tasks = []
+        for w in range(workers):                                # strided shares: cheap and expensive regions of the
+            idx = list(range(w, len(starts), workers))         # start grid are dealt evenly
+            tasks.append((self, idx, [starts[i] for i in idx], screen[idx], (first + w) % ndev, w))
+        results = [None] * len(starts)
+        with mp.get_context(method).Pool(workers) as pool:
+            for idx, part in pool.imap_unordered(_worker_scan, tasks):
+                for i, r in zip(idx, part):
+                    results[i] = r
+        self.scan_stats = dict(workers=workers, devices=min(ndev, workers))
+        return results
+
+    def optimize(self):
+        """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
+        starts = self.start_grid()
+        screen = self._prescreen(starts)
         best = None
-        for x0, res, norm in results:
+        for x0, res, norm in self._scan(starts, screen):
             print('x0={}, x={}, norm={}'.format(x0, res.x if res else None, norm))
-            sys.stdout.flush()
             if best is None or norm < best[2]:
                 best = (x0, res, norm)
-        if pool is not None:
-            pool.close()
-            pool.join()
+        sys.stdout.flush()
         bestx0, bestres, bestnorm = best
         if self.args.Ngrid_high != self.args.Ngrid_low:
             print()

@@ -14,8 +14,9 @@ import np_oracle as O
 class OracleContext:
     instances = 0
 
-    def __init__(self, dim, cos_kappa, s2, kcomp, Y=1.0, Z=1.0, device=0):
+    def __init__(self, dim, cos_kappa, s2, kcomp, Y=1.0, Z=1.0, device=0, devices=None):
         self.dim = dim
+        self.devices = list(devices) if devices else [device]
         self.ncoef = 7 if dim == 2 else 13
         self.grid = O.Grid.from_tables(dim, [np.ravel(c) for c in cos_kappa], [np.ravel(c) for c in s2],
                                        [np.ravel(c) for c in kcomp], Y, Z)
@@ -53,7 +54,9 @@ class OracleContext:
                                  [g.kcomp[0].ravel()[sl]] + [c.ravel() for c in g.kcomp[1:]], g.Y, g.Z)
         return sub, (self.w if np.ndim(self.w) == 0 else self.w[sl])
 
-    def objective_batch(self, coeffs, x_begin=0, x_end=None):
+    def objective_batch(self, coeffs, x_begin=0, x_end=None, x_stride=1, seg_size=0, scan=False, shard="auto"):
+        # segments, the screening variant and sharding change nothing in the results contract
+        assert x_stride == 1, "the oracle-backed context evaluates contiguous slabs only"
         c = np.asarray(coeffs, dtype=float)
         if c.ndim == 1:
             c = c.reshape(1, -1)

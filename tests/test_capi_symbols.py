@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_capi.LIB_PATH)
     for name in header_symbols():
         assert getattr(lib, name) is not None, name
-    assert _capi.load_library().sb200_abi_version() == 1
+    assert _capi.load_library().sb200_abi_version() == _capi.ABI_VERSION == 2
 
 
 def test_cuobjdump_shows_sm100a_only():
