@@ -95,7 +95,7 @@ def coefficients(stencil, params):
 class Grid:
     """The per-axis tables and dense k of one Dispersion object (dispersion.py:268-281, 339-357).
 
-    `xslab=(x0, x1)` keeps only x-planes [x0, x1) of the first axis: the broadcasting
+    `xslab=(x0, x1[, stride])` keeps only x-planes range(x0, x1, stride) of the first axis: the broadcasting
     formulae below work on any table length, which is how grids too large for one
     NumPy array are evaluated slab by slab.
     """
@@ -103,7 +103,7 @@ class Grid:
     def __init__(self, dim, N, Y=1.0, Z=1.0, xslab=None):
         self.dim, self.N, self.Y, self.Z = dim, N, Y, (Z if dim == 3 else 1.0)
         x = np.linspace(0, np.pi, N)
-        xs = x if xslab is None else x[xslab[0]:xslab[1]]
+        xs = x if xslab is None else x[slice(*xslab)]     # (x0, x1) or (x0, x1, stride)
         if dim == 2:
             self.kappa = (xs.reshape(-1, 1), x.reshape(1, -1))
             self.kcomp = (self.kappa[0], self.kappa[1] / Y)

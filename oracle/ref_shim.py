@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference from /root/reference or baseline/_ref.
 
 The reference (Ablinne/optimize-stencil) is pure Python but no longer imports on
 NumPy >= 2 (it uses np.asfarray / np.asscalar, removed upstream) -- SURVEY.md
@@ -13,7 +13,20 @@ import os
 import sys
 import importlib
 
-REFERENCE_ROOT = os.environ.get("OPTSTENCIL_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """/root/reference (this container) or baseline/_ref (oracle/install_reference.sh: the same files, pip-installed
+    where they can travel to the GPU box)."""
+    cands = [os.environ.get("OPTSTENCIL_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "extended_stencil")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():

@@ -1,49 +1,71 @@
-"""The bench line the driver parses: keys of the JSON contract, checked on the committed line of the last
-GPU run (profiles/) and on the static pieces of bench.py that do not need a GPU."""
-import glob
+"""bench.py really runs: the CPU (reference) arm here, the GPU arm under -m gpu -- small sizes, the full JSON contract."""
 import json
 import os
+import subprocess
+import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
 
 
-def latest_bench_line():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v*.json")),
-                   key=lambda f: (len(os.path.basename(f)), os.path.basename(f)))
-    single = [f for f in files if "_n" not in os.path.basename(f)]
-    assert single, "no committed bench line under profiles/"
-    return json.load(open(single[-1])), single[-1]
+def run_bench(*args, timeout=900):
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(args), capture_output=True, text=True,
+                         timeout=timeout, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout[-2000:]          # ONE JSON line on stdout, nothing else
+    return json.loads(lines[0])
 
 
-def test_committed_bench_line_follows_the_contract():
-    line, path = latest_bench_line()
-    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
-        assert key in line, (path, key)
-    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["higher_is_better"] is True
-    assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
+def test_reference_arm_runs_and_keeps_the_contract():
+    line = run_bench("--impl", "reference", "--grid", "48", "--steps", "2", "--warmup", "1")
+    assert BASE_KEYS <= set(line) and line["impl"] == "reference"
+    assert line["metric"].startswith("k-point*candidate objective evals/s") and line["unit"] == "evals/s"
+    assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] > 0
+    assert line["e2e"] == dict(value=line["value"], unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert "workload" in line["config"] and "model" not in line["config"]
-    assert line["gpu_launches"] >= line["steps"] > 0
-    e2e = line["e2e"]
-    assert e2e["unit"] == line["unit"] and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
-    assert 0.5 * line["value"] <= e2e["value"] <= 1.01 * line["value"]
-    roof = line["roofline"]
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
-        assert key in roof, key
-    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
-    # achieved = algorithmic flop per launch / the kernel's launch duration
-    assert abs(roof["achieved"] - roof["evals_per_launch"] * roof["flop_per_eval"] / (roof["launch_ms"] * 1e-3) / 1e12) < 1e-6
-    cpu = line["cpu_baseline"]
-    assert cpu["kind"] in ("port", "reference") and cpu["cores"] >= 1 and cpu["value"] > 0 and cpu["sample"]
-    clocks = line["clocks"]
-    assert clocks["sm_mhz"] > 0.9 * clocks["sm_max_mhz"]
-    assert not set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # both arms describe the workload with the same config dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    a = argparse.Namespace(batch=4096, grid=48, gpus=1)
+    assert line["config"] == bench.config_dict(a)
 
 
-def test_traffic_file_matches_the_committed_profile():
-    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    line, _ = latest_bench_line()
-    assert line["roofline"]["traffic"] is None or line["roofline"]["traffic"] > 0
-    assert t["objective_kernel_dram_bytes_per_launch"] > 0 and 15 < t["objective_kernel_fp64_inst_per_eval"] < 61
-    src = t["source"].split(":")[0]
-    assert os.path.exists(os.path.join(ROOT, src)), src
+def test_other_ranks_of_the_reference_arm_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_arm_runs_and_keeps_the_contract():
+    line = run_bench("--batch", "64", "--grid", "64", "--grid5", "96", "--steps", "2", "--warmup", "3")
+    assert BASE_KEYS | {"roofline", "clocks", "parity", "extra"} <= set(line)
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["gpu_launches"] == 2
+    assert line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 13 * 8 and line["e2e"]["d2h_bytes_per_step"] == 4 * 64 * 8
+    assert "norm_batch" in line["e2e"]["api"]
+    r = line["roofline"]
+    assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 30 < r["peak"] < 39
+    p = line["parity"]
+    assert p["n"] == 8 and p["max_rel_S"] <= 1e-12 and p["extrema_bitwise"] is True
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0
+    x = line["extra"]
+    assert set(x) == {"config1", "config2", "config3_scan", "config3_optimize", "config5_slabs"}
+    assert all("error" not in v for v in x.values()), x
+    assert x["config2"]["omega_max_rel_err"] <= 1e-13 and x["config2"]["norm_rel_err"] <= 1e-12
+    assert x["config3_scan"]["variants_identical"] and x["config3_scan"]["parity"]["extrema_bitwise"]
+    assert x["config5_slabs"]["parity"]["extrema_bitwise"] and x["config5_slabs"]["parity"]["max_rel_S"] <= 1e-12
+    assert abs(x["config1"]["norm_minus_reference"]) <= 3e-6

@@ -349,6 +349,91 @@ def test_fd_memo_follows_the_weight(es):
     assert np.max(np.abs(g2 - 2 * g1)) <= 1e-6 * np.max(np.abs(g1))   # differences of doubled sums: same to FD noise
 
 
+def test_lockstep_scan_prints_what_the_sequential_scan_prints(es, capsys):
+    """All searches concurrently with one (segmented) launch per round vs one search after the other: same lines,
+    same result, same evaluated points, far fewer launches.  (GPU bit-identity of the segments themselves:
+    tests/test_gpu_round2.py.)"""
+    runs = {}
+    for flag in (False, True):
+        es.Optimize.lockstep = flag
+        try:
+            opt = es.Optimize(default_args(div_free=True, dtrange=[0.6718, 1.0], N=4, Ngrid_low=30, Ngrid_high=60))
+            x, f = opt.optimize()
+        finally:
+            es.Optimize.lockstep = True
+        runs[flag] = (x, f, capsys.readouterr().out, dict(opt.dispersion.stats), opt.scan_stats)
+    assert runs[True][2] == runs[False][2] and runs[True][2].count("x0=") == 16 + 2
+    assert np.array_equal(runs[True][0], runs[False][0]) and runs[True][1] == runs[False][1]
+    assert runs[True][3] == runs[False][3]
+    assert runs[True][4]["launches"] * 3 < runs[True][3]["launches"] and runs[False][4] == {}
+
+
+def test_lockstep_propagates_errors_from_a_search(es, monkeypatch):
+    opt = es.Optimize(default_args(div_free=True, dtrange=[0.6718, 1.0], N=3, Ngrid_low=20, Ngrid_high=20))
+
+    def boom(self, dispersion, constraints, x0):
+        dispersion.norm(x0)                  # take part in a round first, then fail
+        if x0[1] > -0.5:
+            raise ValueError("search failed on purpose")
+        return es.Optimize._minimize.__wrapped__(self, dispersion, constraints, x0)
+
+    boom.__wrapped__ = es.Optimize._minimize
+    monkeypatch.setattr(es.Optimize, "_minimize", boom)
+    with pytest.raises(ValueError, match="on purpose"):
+        opt.optimize()
+
+
+def test_constraint_return_types_follow_the_reference(es):
+    """dispersion.py:299-307 / 377-385: a negative grid minimum is returned as the NumPy scalar np.min gave, the
+    corner minimum as the shape-(1,) array the record fields give; dt_ok passes a negative stencil_ok through."""
+    d = es.Dispersion2D(1, 20, es.StencilFree2D())
+    ok = [0.5, 0.05, -0.02, -0.1, -0.12]
+    bad = [0.3, 0.3, -0.3, 0.3, 0.7]                   # tests/test_dispersion.py:39-47 (negative sqrtarg)
+    assert isinstance(d.stencil_ok(ok), np.ndarray) and d.stencil_ok(ok).shape == (1,)
+    assert isinstance(d.dt_ok(ok), np.ndarray) and d.dt_ok(ok).shape == (1,)
+    s = d.stencil_ok(bad)
+    assert isinstance(s, np.float64) and np.ndim(s) == 0 and s < 0
+    t = d.dt_ok(bad)
+    assert isinstance(t, np.float64) and t == s
+    assert "%s" % s == "%s" % np.float64(s) and "[" not in "%s" % s     # prints like the reference's scalar
+
+
+def test_fd_points_cost_one_launch_when_only_the_iterate_is_cached(es):
+    """x cached without its neighbours (a start taken from a batch, prefetch off) must cost ONE launch
+    of the n + 1 points, not one launch per neighbour -- and the difference never mixes two launches."""
+    d = es.Dispersion2D(1, 30, es.StencilIsotropicDivFree2D())
+    x = np.array([0.7, -0.02])
+    d.evaluate_batch(np.array([x, x + 0.01]))          # x is cached, its neighbours are not
+    launches, evaluated = d.stats["launches"], d.stats["evaluated"]
+    g = d.norm_fd(x)
+    assert d.stats["launches"] == launches + 1 and d.stats["evaluated"] == evaluated + 3
+    d.stencil_ok_fd(x), d.dt_ok_fd(x)
+    assert d.stats["launches"] == launches + 1
+    fresh = es.Dispersion2D(1, 30, es.StencilIsotropicDivFree2D())
+    np.testing.assert_array_equal(g, fresh.norm_fd(x))
+    d2 = es.Dispersion2D(1, 30, es.StencilIsotropicDivFree2D())
+    d2.fd_prefetch = False
+    d2.norm(x)
+    assert d2.stats["evaluated"] == 1
+    np.testing.assert_array_equal(d2.norm_fd(x), g)
+    assert d2.stats["launches"] == 2 and d2.stats["evaluated"] == 4
+
+
+def test_views_share_the_context_and_keep_their_own_cache(es):
+    d = es.Dispersion3D(1.0, 1.0, 10, es.StencilDivFree3D())
+    es.weight_functions["xaxis_soft"](0.4)(d)
+    v1, v2 = d.view(), d.view()
+    p = [0.3, -0.10, -0.60, 0.2]
+    assert v1.norm(p) == v2.norm(p) == d.norm(p)
+    assert v1._context() is d._context() and v1._cache is not v2._cache
+    assert v1.stats["launches"] == 1 and d.stats["launches"] == 1
+    v1.parameters = p
+    assert d.parameters is None or not np.array_equal(d.parameters, [9, 9, 9, 9])
+    calls = []
+    v3 = d.view(lambda C: calls.append(len(C)) or d._context().objective_batch(C))
+    assert v3.norm(p) == d.norm(p) and calls == [5]
+
+
 def test_start_grid(es):
     opt = es.Optimize(default_args(N=2, scan_dt=False))
     starts = opt.start_grid()

@@ -103,3 +103,21 @@ def test_slabs_tile_the_grid():
     parts = [O.device_contract(O.Grid(3, 24, xslab=(a, b)), c) for a, b in ((0, 5), (5, 16), (16, 24))]
     assert relerr(sum(p[0] for p in parts), full[0]) < 1e-13
     assert min(p[1] for p in parts) == full[1] and max(p[2] for p in parts) == full[2]
+
+
+def test_slabwise_reference_driver_equals_the_reference():
+    """oracle/ref_slab.py (bench.py's CPU arm: the unmodified reference's own Dispersion3D.norm over x-slabs with
+    overridden tables) against the reference evaluated on the whole grid."""
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("the unmodified reference is not present (neither /root/reference nor baseline/_ref)")
+    import ref_slab
+    es = ref_shim.load_reference()
+    rng = np.random.default_rng(8)
+    xc = np.array([0.5, .02, .03, .01, .02, .03, .01, -.02, -.03, -.01])
+    d = es.Dispersion3D(1.0, 1.0, 30, es.StencilFree3D())
+    for _ in range(3):
+        p = xc + 1e-3 * rng.standard_normal(10)
+        whole = float(d.norm(p))
+        for slab in (30, 7, 1):
+            assert abs(ref_slab.norm_slabwise(p, 30, slab) - whole) <= 1e-13 * whole

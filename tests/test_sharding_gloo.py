@@ -23,9 +23,9 @@ def coeff_batch(B):
     return np.stack([O.coefficients("StencilFree3D", p) for p in P])
 
 
-def oracle_evaluator(block, x_begin, x_end):
+def oracle_evaluator(block, x_begin, x_end, x_stride=1):
     out = np.empty((4, block.shape[0]))
-    grid = O.Grid(3, N, xslab=(x_begin, x_end))
+    grid = O.Grid(3, N, xslab=(x_begin, x_end, x_stride))
     for b in range(block.shape[0]):
         S, amin, amax, nn = O.device_contract(grid, block[b].numpy())
         out[:, b] = (S, amin if amin < 0 else 0.0, max(amax, 0.0), nn)
@@ -55,7 +55,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("mode,B", [("candidates", 7), ("candidates", 2), ("slabs", 5)])
+@pytest.mark.parametrize("mode,B", [("candidates", 7), ("candidates", 2), ("candidates", 8), ("slabs", 5),
+                                    ("slabs-contiguous", 5)])
 def test_world_size_2(mode, B):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -98,4 +99,5 @@ def test_combine_slab_partials_propagates_nan_and_order():
     assert out[1][0] == -0.5 and np.isnan(out[1][1]) and np.isnan(out[2][1])
     assert out[2][0] == 4.0 and out[3][0] == 2.0 and out[3][1] == 1.0
     single = sharding.ShardedObjective(oracle_evaluator, nx=N, mode="slabs")
-    assert (single.rank, single.world) == (0, 1) and single.my_planes() == (0, N)
+    assert (single.rank, single.world) == (0, 1) and single.my_planes() == (0, N, 1)
+    assert sharding.ShardedObjective(oracle_evaluator, nx=N, mode="slabs-contiguous").my_planes() == (0, N, 1)
