@@ -289,6 +289,11 @@ def parity_against_c_oracle(N, coeffs, rows, got):
 
 
 def run_gpu_arm(a):
+    # Keep stdout to the one JSON line: anything libraries print while the communicator comes up (NCCL's
+    # version banner, debug output) is sent to stderr until the line itself is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     env = Env(a)
     torch, dist = env.torch, env.dist
     import optimize_stencil_b200 as sb
@@ -296,11 +301,6 @@ def run_gpu_arm(a):
     from optimize_stencil_b200.extended_stencil import StencilFree3D, Dispersion3D
 
     rank, world, local, device = env.rank, env.world, env.local, env.device
-    # Keep stdout to the one JSON line: anything libraries print while the communicator comes up (NCCL's
-    # version banner, debug output) is sent to stderr until the line itself is printed.
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
 
     N, B = a.grid, a.batch
     stencil = StencilFree3D()
