@@ -42,6 +42,10 @@
 #include "dispersion_kernels.cuh"
 #include <climits>
 
+#ifndef SB200_ALLMID_VIMAX
+#define SB200_ALLMID_VIMAX (SB200_INNER != 0)   // "every chain is MID" from three-input integer maxima of the high words of v^2
+#endif
+
 namespace sb200 {
 
 // sqrtarg at one k-point from the per-axis tables, reference order (dispersion.py:394-398).  Rare path.
@@ -220,6 +224,9 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                 // W = 2 dt^2 A (regrouped), v = W - 1 = 2 s^2 - 1, t = v^2, hk = pi/2 - k dt
                 double W[J], A[J], v[J], t[J], e[J], hk[J], w[U], kr[U];
                 bool need = false, all_mid = true;
+#if SB200_INNER
+                bool all_inner = false;
+#endif
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double* r = row + u * ROW;
@@ -239,9 +246,25 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                         v[j] = __dadd_rn(W[j], -1.0);
                         hk[j] = fma(-k, dtc[c], kPi2);
                         t[j] = __dmul_rn(v[j], v[j]);
+#if !SB200_ALLMID_VIMAX
                         all_mid = all_mid && ((unsigned int)__double2hiint(t[j]) <= 0x3fd00000u);   // |v| <= 1/2, not NaN
+#endif
                     }
                 }
+#if SB200_ALLMID_VIMAX
+                {   // |v| <= 1/2 on every chain <=> the largest high word of v^2 (as unsigned; a NaN is larger still) <= 1/4:
+                    // three-input integer maxima instead of one compare per chain
+                    unsigned int hmax = (unsigned int)__double2hiint(t[0]);
+#pragma unroll
+                    for (int j = 1; j + 1 < J; j += 2)
+                        hmax = __vimax3_u32(hmax, (unsigned int)__double2hiint(t[j]), (unsigned int)__double2hiint(t[j + 1]));
+                    if (J % 2 == 0) hmax = max(hmax, (unsigned int)__double2hiint(t[J - 1]));
+                    all_mid = hmax <= 0x3fd00000u;
+#if SB200_INNER
+                    all_inner = hmax <= SB200_INNER_HI;
+#endif
+                }
+#endif
                 // Rare: redo the iteration in the reference's operation order and let the exact values (and
                 // only those) into the extrema.  The opaque copies keep the address arithmetic in here.
                 auto redo_exact = [&]() {
@@ -284,8 +307,18 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                 if (redone) redo_exact();
                 if (__all_sync(FULL, all_mid)) {
                     // |v| <= 1/2 for every lane and chain: dt*omega = pi/2 + v f(v^2), no square root
+#if SB200_INNER
+                    // ... and with the shorter series when v^2 is small on every lane and chain (after a redo the
+                    // flag is stale, i.e. false: the full series is always valid)
+                    if (__all_sync(FULL, all_inner && !redone)) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
+                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f_inner(t[j]), hk[j]);
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
+                    }
                 } else {
                     if (SCAN) {
                         // v >= 1 + 2^-12 as a signed compare of high words.  +inf and a positive NaN pass as well: omega

@@ -382,15 +382,17 @@ class Dispersion:
             return np.float64(sok) if e[1] < 0 else np.array([sok])
         return np.array([dtok])
 
-    def omega(self, parameters):
-        """omega(k) on the dense grid, or None when the constraints are violated (dispersion.py:164-196)."""
+    def omega(self, parameters, out=None):
+        """omega(k) on the dense grid, or None when the constraints are violated (dispersion.py:164-196).
+        `out` (not in the reference): an existing float64 array of the grid's shape to fill and return."""
         self.parameters = parameters
         e = self._entry(parameters)
         if e is None:
             return None                      # stencil_ok() is -1 for NaN input (dispersion.py:174-178)
         if not self._gate(e)[2]:
             return None
-        om, _, _, nan = self._context().export(e[4], _capi.SB200_X_OMEGA)
+        kw = {} if out is None else dict(out=out)
+        om, _, _, nan = self._context().export(e[4], _capi.SB200_X_OMEGA, **kw)
         if nan:
             raise ValueError('Encountered NaNs in omega for params', parameters)
         return om

@@ -74,12 +74,16 @@ class OracleContext:
         self.launch_count += 1
         return S, Amin, Amax, nan
 
-    def export(self, coeffs, what=0, x_begin=0, x_end=None):
+    def export(self, coeffs, what=0, x_begin=0, x_end=None, out=None):
         grid, _ = self._slab(x_begin, x_end)
         c = np.asarray(coeffs, dtype=float)
         with np.errstate(invalid="ignore", divide="ignore"):
             A = np.array(np.broadcast_to(O.sqrtarg(grid, c), grid.shape))
-            out = A if what == 1 else (np.sqrt(A) if what == 2 else O.omega_from_sqrtarg(A, c[0]))
+            res = A if what == 1 else (np.sqrt(A) if what == 2 else O.omega_from_sqrtarg(A, c[0]))
+        if out is not None:
+            out[...] = res
+        else:
+            out = res
         amin, amax = A.min(), A.max()
         self.launch_count += 1
         return out, (amin if amin < 0 else 0.0), max(amax, 0.0), int(np.count_nonzero(np.isnan(out)))

@@ -39,3 +39,29 @@ for what, name in ((0, "omega"), (1, "sqrtarg"), (2, "sqrtres")):
     gbs = N ** 3 * 8 / (ms * 1e-3) / 1e9
     print("export %-8s %d^3: %.3f ms  %.1f GB/s written (algorithmic 8 B/point)  %.2f of %s HBM copy peak %.0f GB/s  "
           "%.1f G points/s" % (name, N, ms, gbs, gbs / hbm, "measured" if peaks else "fallback", hbm, N ** 3 / ms / 1e6))
+
+# End to end: Context.export into a fresh NumPy array (kernel + chunked, double-buffered pinned D2H + the host-side
+# copy into the caller's pageable buffer); the rate is what sb200_last_export_stats reports for the call.
+import time  # noqa: E402
+for rep in range(4):
+    t0 = time.perf_counter()
+    om = ctx.export(co, 0)[0]
+    wall = time.perf_counter() - t0
+    nbytes, secs = ctx.last_export_stats
+    print("Context.export(omega) %d^3 -> NumPy: %.1f ms wall, %.1f ms inside sb200_export = %.1f GB/s delivered "
+          "(copy threads: %s)" % (N, 1e3 * wall, 1e3 * secs, nbytes / secs / 1e9, os.environ.get("SB200_COPY_THREADS", "default")))
+    del om
+pinned = torch.empty(N ** 3, dtype=torch.float64).pin_memory()
+for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pinned.copy_(out, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+print("plain D2H of the same field into pinned memory: %.1f ms = %.1f GB/s (the PCIe rate the export can approach)"
+      % (1e3 * dt, N ** 3 * 8 / dt / 1e9))
+dst = np.empty(N ** 3)
+t0 = time.perf_counter()
+np.copyto(dst, pinned.numpy())
+dt = time.perf_counter() - t0
+print("one host thread copying it from pinned into a fresh NumPy array: %.1f ms = %.1f GB/s" % (1e3 * dt, N ** 3 * 8 / dt / 1e9))
