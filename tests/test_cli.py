@@ -43,7 +43,7 @@ def compare(out, golden_lines, tol):
 
 
 @pytest.mark.parametrize("name", ["cli_calc_lehe2d", "cli_calc_lehe3d", "cli_calc_yee_epoch", "cli_calc_pukhov_array",
-                                  "cli_calc_laser2d", "cli_calc_laser3d"])
+                                  "cli_calc_laser2d", "cli_calc_laser3d", "cli_calc_infeasible2d", "cli_calc_infeasible3d"])
 def test_calculate_omega_matches_reference_output(cli, name, capsys):
     text = open(os.path.join(GOLDEN, name + ".txt")).read().splitlines()
     argv = text[0].split()
@@ -78,3 +78,35 @@ def test_write_omega_file_format(cli, tmp_path, capsys):
     assert data[0, 4] == 1.0 and np.all(data[:3, 5] == 1.0)          # vph at k=0 and the vg patch are forced to 1
     ok = data[:, 2] > 0
     assert np.allclose(data[ok, 4], data[ok, 3] / data[ok, 2])
+
+
+@pytest.mark.parametrize("name", ["omega_yee2d", "omega_lehe3d", "omega_soft2d"])
+def test_write_omega_against_the_reference_file(cli, name, tmp_path, capsys, request):
+    """dispersion.py:199-232 -- `--write-omega` files written by the UNMODIFIED reference (oracle/make_golden_cli.py,
+    with the np.vstack shim of SURVEY.md 8c) against ours for the same command line.
+      oracle-backed (CPU): the writer alone is under test (omega comes from the NumPy oracle): BYTE FOR BYTE.
+      cuda: same bytes for everything that does not depend on the last bits of omega (header, layout, the kappa and
+            k columns, the forced 1.0 entries); omega to 1e-13, the derived velocities to 1e-11 (numpy.gradient
+            divides the omega differences by 2h)."""
+    text = open(os.path.join(GOLDEN, name + ".txt")).read().splitlines()
+    out_file = tmp_path / (name + ".dat")
+    argv = [str(out_file) if a == "@OUT@" else a for a in text[0].split()]
+    assert cli.main_calculate(argv) == 0
+    capsys.readouterr()
+    want = open(os.path.join(GOLDEN, name + ".dat"), "rb").read()
+    got = out_file.read_bytes()
+    if "oracle-backed" in request.node.name:
+        assert got == want
+        return
+    wl, gl = want.split(b"\n"), got.split(b"\n")
+    assert len(wl) == len(gl) and wl[0] == gl[0]
+    dim = 3 if b"kz" in wl[0] else 2
+    for a, b in zip(wl[1:], gl[1:]):
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb)
+        if not ta:
+            continue
+        assert ta[:dim + 1] == tb[:dim + 1]                         # kappa columns and k: exact text
+        fa, fb = np.array(ta, dtype=float), np.array(tb, dtype=float)
+        assert abs(fa[dim + 1] - fb[dim + 1]) <= 1e-13 * max(abs(fa[dim + 1]), 1e-300)      # omega
+        assert np.all(np.abs(fa[dim + 2:] - fb[dim + 2:]) <= 1e-11 * np.maximum(np.abs(fa[dim + 2:]), 1.0))

@@ -252,6 +252,13 @@ def run_optimize(es, name, capsys=None):
     dx_ = np.abs(x - z[name + "_x"])
     if name == "xaxis_soft":
         assert np.max(dx_[:3]) <= 2e-3 and dx_[3] <= 0.1, (name, x, z[name + "_x"])
+    elif name == "default":
+        # Config 1.  The bar is MEASURED, not chosen: oracle/config1_spread.py re-runs the unmodified reference with
+        # the last bit of its own `f.sum()` perturbed (+-1 ulp, reversed summation order, correctly rounded sum,
+        # random last-bit jitter); its optimum then moves by up to 1.5e-4 in the coefficients and 3.6e-7 in the norm
+        # (profiles/r02_config1_spread.txt).  Three times that spread is "agreement to SciPy's tolerance" here.
+        assert np.max(dx_) <= 3 * 1.5e-4, (name, x, z[name + "_x"])
+        assert abs(fmin - ref) <= 3 * 3.636e-7, (name, fmin, ref)
     else:
         assert np.max(dx_) <= 1e-3, (name, x, z[name + "_x"])
     return opt, x, fmin, z
