@@ -309,7 +309,8 @@ def run_gpu_arm(a):
     params = workload_parameters(B)
     coeffs_host = stencil.coefficients_batch(params)
     coeffs_dev = torch.from_numpy(coeffs_host).to(device)
-    sharded = sharding.ShardedObjective(sharding.device_evaluator(ctx), nx=N, mode="candidates")
+    # a throughput launch: the shorter asin series (SB200_F_FAST), like Dispersion3D.norm_batch picks for this size
+    sharded = sharding.ShardedObjective(sharding.device_evaluator(ctx, fast=True), nx=N, mode="candidates")
 
     peak = sb.fp64_peak_tflops(local, 0.5)   # measured DFMA roofline denominator, same box, same run
 
@@ -420,7 +421,7 @@ def run_gpu_arm(a):
         except Exception:
             traffic = inst = None
     roofline = dict(bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                    traffic=traffic, kernel="sb200::objective_kernel_fa<4,true,0,false>",
+                    traffic=traffic, kernel="sb200::objective_kernel_fa<4,true,0,false,0>",
                     flop_per_eval=F_ALG_3D, evals_per_launch=launch_evals, launch_ms=launch_ms,
                     peak_source="DFMA microbenchmark (sb200_fp64_peak: best of several chains x resident-warps shapes) "
                                 "measured in this run on this GPU; MEASURED_PEAKS.json has no FP64 entry",
@@ -576,7 +577,7 @@ def extra_config3_scan(a, env, sb):
     Cd = torch.from_numpy(C).to(env.device)
     out = {}
     for name, scan in (("plain", False), ("screening", True)):
-        sh = sharding.ShardedObjective(sharding.device_evaluator(ctx, scan=scan), nx=N, mode="candidates")
+        sh = sharding.ShardedObjective(sharding.device_evaluator(ctx, scan=scan, fast=True), nx=N, mode="candidates")
         ms, res = timed_steps(env, lambda: sh.evaluate(Cd))
         out[name] = (ms, res.cpu().numpy())
     a0, a1 = out["plain"][1], out["screening"][1]
@@ -639,7 +640,7 @@ def extra_config5(a, env, sb):
                         % (N, env.world), grid=[N] * 3, candidates=1, unit=UNIT)
     results = {}
     for mode in (("slabs", "slabs-contiguous") if env.world > 1 else ("slabs",)):
-        sh = sharding.ShardedObjective(sharding.device_evaluator(ctx), nx=N, mode=mode,
+        sh = sharding.ShardedObjective(sharding.device_evaluator(ctx, fast=True), nx=N, mode=mode,
                                        combine=sharding.device_combiner(ctx))
         ms, res = timed_steps(env, lambda: sh.evaluate(Cd), steps=10, warmup=3)
         results[mode] = res.cpu().numpy()[:, 0]
@@ -653,7 +654,7 @@ def extra_config5(a, env, sb):
     if env.rank == 0:
         # parity: a sample of x-plane ranges through the same entry point on this rank alone against the C oracle,
         # and the sharded sum against this rank's own whole-grid evaluation
-        S1, lo1, hi1, nn1 = ctx.objective_batch(C)
+        S1, lo1, hi1, nn1 = ctx.objective_batch(C, fast=True)
         rec["sharded_vs_one_gpu_rel"] = abs(got[0] - S1[0]) / abs(S1[0])
         assert got[1] == lo1[0] and got[2] == hi1[0] and rec["sharded_vs_one_gpu_rel"] <= 1e-13, (got, S1, lo1, hi1)
         rel, exact = 0.0, True

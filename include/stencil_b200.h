@@ -145,9 +145,15 @@ int sb200_objective_batch(sb200_ctx* ctx, const double* coeffs, int64_t nbatch,
  *             its candidates skips the evaluation: omega is NaN there whatever the bits).  Results are identical
  *             to the plain variant; it is faster when most candidates violate the CFL limit and ~1.5 % slower
  *             otherwise.  SB200_F_AUTO_SCAN (host-buffer entry points only): decide per call from the
- *             candidates' corner values. */
+ *             candidates' corner values.
+ *             SB200_F_FAST: evaluate asin with the shorter series (relative error 3.7e-15 instead of 2.3e-16; omega
+ *             stays 25x inside the 1e-13 bar, the objective 500x inside 1e-12) -- 4 % more throughput, meant for
+ *             large batches.  Without it the sums agree with NumPy's to a few 1e-16, which keeps an SLSQP search
+ *             on the reference's trajectory for as long as floating point allows; the screening variant always
+ *             uses the shorter series. */
 #define SB200_F_SCAN       1
 #define SB200_F_AUTO_SCAN  2
+#define SB200_F_FAST       4
 typedef struct sb200_batch_opts {
     int32_t x_begin, x_stride, n_planes;
     int32_t flags;

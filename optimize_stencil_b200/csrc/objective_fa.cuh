@@ -85,7 +85,9 @@ struct RowLayoutFA {
 // takes NaN directly; the extrema were already dealt with by then.  Results are bit-identical to the plain variant;
 // it is a separate instantiation because the extra merge point costs the plain MID loop two register moves per
 // iteration (measured: 682 -> 672 G evals/s on the 4096 x 512^3 batch).
-template <int C, bool UNIT, int WK, bool SCAN>
+//
+// PREC: 1 the precise series (search launches), 0 the fast one (throughput launches) -- dispersion_kernels.cuh.
+template <int C, bool UNIT, int WK, bool SCAN, int PREC>
 __global__ void __launch_bounds__(SB200_MAXTHREADS, (C <= 4 ? SB200_MINBLOCKS_C4 : SB200_MINBLOCKS_C8))
 objective_kernel_fa(const GridDev g, const BatchArgs a) {
     constexpr int ROW = RowLayoutFA<C>::ROW;
@@ -312,12 +314,12 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                     // flag is stale, i.e. false: the full series is always valid)
                     if (__all_sync(FULL, all_inner && !redone)) {
 #pragma unroll
-                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f_inner(t[j]), hk[j]);
+                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f_inner<PREC>(t[j]), hk[j]);
                     } else
 #endif
                     {
 #pragma unroll
-                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f(t[j]), hk[j]);
+                        for (int j = 0; j < J; ++j) e[j] = fma(v[j], asin_f<PREC>(t[j]), hk[j]);
                     }
                 } else {
                     if (SCAN) {
@@ -339,7 +341,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);             // dt^2 A
                     // |v| <= sqrt(3)/2, or -1 + 2^-21 < v < -1/2, on every lane and chain: out of reach of every guard
-                    if (!dev_try_nosqrt<C, J>(v, hk, e, FULL) && !dev_try_low<C, J, true>(z2, v, kr, e, cand, FULL)) {
+                    if (!dev_try_nosqrt<C, J, PREC>(v, hk, e, FULL) && !dev_try_low<C, J, true, PREC>(z2, v, kr, e, cand, FULL)) {
                         if (!redone) {
                             // v <= -1 + 2^-21 (sqrtarg may be negative or a negative NaN) or v within
                             // [1 - 2^-9 - 2^-12, 1 + 2^-12): the EXACT class needs the reference's bits there.
@@ -359,7 +361,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                                 for (int j = 0; j < J; ++j) A[j] = __dmul_rn(W[j], cand[j % C].ic2);   // read where s > 1 only
                             }
                         }
-                        dev_high_or_any<C, J>(A, z2, v, hk, kr, e, cand, FULL);
+                        dev_high_or_any<C, J, PREC>(A, z2, v, hk, kr, e, cand, FULL);
                     }
                 }
 #pragma unroll

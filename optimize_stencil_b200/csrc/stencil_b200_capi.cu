@@ -406,6 +406,7 @@ struct Request {
     long long seg = 0;                     // candidates per segment (== B when un-segmented)
     long long nseg = 1;
     bool scan = false;
+    bool fast = false;                     // the shorter asin series (throughput launches); screening implies it
 };
 
 struct Plan {
@@ -462,33 +463,37 @@ Plan make_plan(const sb200_ctx* ctx, const Request& r) {
 }
 
 template <int C>
-cudaError_t launch_objective(const sb200_ctx* ctx, const Plan& p, const BatchArgs& a, bool scan, cudaStream_t st) {
+cudaError_t launch_objective(const sb200_ctx* ctx, const Plan& p, const BatchArgs& a, const Request& r, cudaStream_t st) {
     dim3 grid((unsigned)(p.n_chunks * p.n_ztiles), (unsigned)p.n_xchunks, (unsigned)p.n_ychunks), block(p.TZ);
 #if SB200_FAST_A
-#define SB200_KERNEL(UNIT, WK, SCAN) objective_kernel_fa<C, UNIT, WK, SCAN>
+#define SB200_KERNEL(UNIT, WK, SCAN, PREC) objective_kernel_fa<C, UNIT, WK, SCAN, PREC>
 #else
-#define SB200_KERNEL(UNIT, WK, SCAN) objective_kernel<C, UNIT, WK>
+#define SB200_KERNEL(UNIT, WK, SCAN, PREC) objective_kernel<C, UNIT, WK>
 #endif
-#define SB200_LAUNCH(UNIT, WK, SCAN)                                                                        \
+#define SB200_LAUNCH(UNIT, WK, SCAN, PREC)                                                                  \
     do {                                                                                                    \
-        auto kern = SB200_KERNEL(UNIT, WK, SCAN);                                                           \
+        auto kern = SB200_KERNEL(UNIT, WK, SCAN, PREC);                                                     \
         if (p.smem > 48 * 1024) {                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
             if (e != cudaSuccess) return e;                                                                 \
         }                                                                                                   \
         kern<<<grid, block, p.smem, st>>>(ctx->g, a);                                                       \
     } while (0)
-#define SB200_LAUNCH_W(UNIT, SCAN)                                                                          \
+#define SB200_LAUNCH_W(UNIT, SCAN, PREC)                                                                    \
     do {                                                                                                    \
-        if (ctx->wkind == 0) SB200_LAUNCH(UNIT, 0, SCAN);                                                   \
-        else if (ctx->wkind == 1) SB200_LAUNCH(UNIT, 1, SCAN);                                              \
-        else SB200_LAUNCH(UNIT, 2, SCAN);                                                                   \
+        if (ctx->wkind == 0) SB200_LAUNCH(UNIT, 0, SCAN, PREC);                                             \
+        else if (ctx->wkind == 1) SB200_LAUNCH(UNIT, 1, SCAN, PREC);                                        \
+        else SB200_LAUNCH(UNIT, 2, SCAN, PREC);                                                             \
     } while (0)
-    if (ctx->unit_cell) {
-        if (scan) SB200_LAUNCH_W(true, true); else SB200_LAUNCH_W(true, false);
-    } else {
-        if (scan) SB200_LAUNCH_W(false, true); else SB200_LAUNCH_W(false, false);
-    }
+    // three variants per (C, cell, weight): screening (always the fast series), fast, precise
+#define SB200_LAUNCH_V(UNIT)                                                                                \
+    do {                                                                                                    \
+        if (r.scan) SB200_LAUNCH_W(UNIT, true, 0);                                                          \
+        else if (r.fast) SB200_LAUNCH_W(UNIT, false, 0);                                                    \
+        else SB200_LAUNCH_W(UNIT, false, 1);                                                                \
+    } while (0)
+    if (ctx->unit_cell) SB200_LAUNCH_V(true); else SB200_LAUNCH_V(false);
+#undef SB200_LAUNCH_V
 #undef SB200_LAUNCH_W
 #undef SB200_LAUNCH
 #undef SB200_KERNEL
@@ -521,6 +526,7 @@ static int resolve_request(sb200_ctx* ctx, int64_t B, const sb200_batch_opts* o,
     r->seg = seg > 0 ? seg : B;
     r->nseg = B / r->seg;
     r->scan = (flags & SB200_F_SCAN) != 0;
+    r->fast = (flags & SB200_F_FAST) != 0;
     return SB200_OK;
 }
 
@@ -558,10 +564,10 @@ static int objective_device_impl(sb200_ctx* ctx, const double* d_coeffs, int64_t
     a.out = d_out;
     cudaError_t e;
     switch (p.C) {
-        case 1: e = launch_objective<1>(ctx, p, a, r.scan, st); break;
-        case 2: e = launch_objective<2>(ctx, p, a, r.scan, st); break;
-        case 4: e = launch_objective<4>(ctx, p, a, r.scan, st); break;
-        default: e = launch_objective<8>(ctx, p, a, r.scan, st); break;
+        case 1: e = launch_objective<1>(ctx, p, a, r, st); break;
+        case 2: e = launch_objective<2>(ctx, p, a, r, st); break;
+        case 4: e = launch_objective<4>(ctx, p, a, r, st); break;
+        default: e = launch_objective<8>(ctx, p, a, r, st); break;
     }
     if (e != cudaSuccess) {
         ctx->tickets_dirty = true;
@@ -1118,7 +1124,7 @@ extern "C" int sb200_fp64_peak(int32_t device, double seconds, double* tflops) {
     PK(cudaSetDevice(device));
     cudaDeviceProp prop;
     PK(cudaGetDeviceProperties(&prop, device));
-    const int threads = 256, iters = 4096;
+    const int threads = 256;
     double* d = nullptr;
     PK(cudaMalloc((void**)&d, (size_t)prop.multiProcessorCount * 8 * threads * sizeof(double)));
     cudaEvent_t e0, e1;
@@ -1126,29 +1132,33 @@ extern "C" int sb200_fp64_peak(int32_t device, double seconds, double* tflops) {
     if (!(seconds > 0)) seconds = 0.2;
     // shapes: (chains per thread, CTAs of 256 threads per SM).  4 chains x 4 warps per sub-partition and
     // 8 chains x 2 or 4 warps reach one warp instruction per 2.00 cycles in tools/ubench_latency.cu.
+    // Few, long launches (one warm-up and three timed ones per shape, ~seconds/20 each): a launch list of a
+    // program that calls this stays readable.
     struct Shape { int chains, ctas_per_sm; };
     const Shape shapes[] = {{8, 2}, {4, 2}, {8, 1}, {4, 4}, {8, 4}};
     const bool verbose = getenv("SB200_PEAK_VERBOSE") != nullptr;
     double best = 0.0;
     for (const Shape& s : shapes) {
         const int blocks = prop.multiProcessorCount * s.ctas_per_sm;
-        const double flop_per_launch = 2.0 * 64.0 * iters * (double)blocks * threads;
+        // iterations for about seconds/20 per launch at the nominal rate (64 DFMA per thread and iteration)
+        const double per_iter = 2.0 * 64.0 * (double)blocks * threads;
+        const int iters = (int)std::max(1024.0, std::min(4.0e6, seconds / 20.0 * 37.0e12 / per_iter));
+        const double flop_per_launch = per_iter * iters;
         auto launch = [&]() {
             if (s.chains == 8) dfma_peak_kernel<8><<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
             else dfma_peak_kernel<4><<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
         };
-        for (int i = 0; i < 2; ++i) launch();
+        launch();
         PK(cudaDeviceSynchronize());
-        double spent = 0.0, here = 0.0;
-        while (spent < seconds / 5) {
+        double here = 0.0;
+        for (int rep = 0; rep < 3; ++rep) {
             PK(cudaEventRecord(e0));
-            for (int i = 0; i < 4; ++i) launch();
+            launch();
             PK(cudaEventRecord(e1));
             PK(cudaEventSynchronize(e1));
             float ms = 0.f;
             PK(cudaEventElapsedTime(&ms, e0, e1));
-            here = std::max(here, 4.0 * flop_per_launch / (ms * 1e-3) / 1e12);
-            spent += ms * 1e-3;
+            here = std::max(here, flop_per_launch / (ms * 1e-3) / 1e12);
         }
         if (verbose) fprintf(stderr, "sb200_fp64_peak: %d chains x %d CTAs/SM: %.2f TFLOP/s\n", s.chains, s.ctas_per_sm, here);
         best = std::max(best, here);

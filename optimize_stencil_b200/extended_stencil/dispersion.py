@@ -248,7 +248,8 @@ class Dispersion:
     def _raw_batch(self, P):
         """(B, dof) parameters -> (S, Amin, Amax, nan, C) via ONE launch; fills the cache."""
         C = self.stencil.coefficients_batch(P)
-        S, Amin, Amax, nan = self._launch(C)
+        # the precise series, whatever the size: these are the values a search differentiates
+        S, Amin, Amax, nan = self._launch(C) if self._submit is not None else self._launch(C, fast=False)
         self.stats['launches'] += 1
         self.stats['evaluated'] += len(P)
         self._launch_id += 1

@@ -187,7 +187,7 @@ class _LockStep:
                 parent, seg = reqs[0].parent, len(reqs[0].C)
                 C = np.concatenate([r.C for r in reqs]) if len(reqs) > 1 else reqs[0].C
                 ctx = parent._context(len(C) * parent._grid_points())
-                S, Amin, Amax, nan = ctx.objective_batch(C, seg_size=seg if len(reqs) > 1 else 0)
+                S, Amin, Amax, nan = ctx.objective_batch(C, seg_size=seg if len(reqs) > 1 else 0, fast=False)
                 self.launches += 1
                 self.rows += len(C)
                 for n, r in enumerate(reqs):
@@ -250,13 +250,27 @@ class _LockStep:
         return results
 
 
-def _worker_scan(task):
-    """Entry point of a worker process: one share of the start grid, on one GPU."""
-    opt, indices, starts, screen, device, rank = task
+_WORKER = {}
+
+
+def _worker_init(opt, first_device, ndev):
+    """Once per worker process: the Optimize object (its Dispersion objects re-create their device contexts lazily,
+    like the reference's pickled objects re-run init2) on this worker's GPU -- workers are dealt round robin over
+    the visible devices."""
+    import multiprocessing as mp
+    ident = mp.current_process()._identity
+    rank = (ident[0] - 1) if ident else 0
+    device = (first_device + rank) % ndev
     for d in (opt.dispersion, opt.dispersion_high):
         d.device = device
         d.devices = [device]
-    return indices, opt._scan_local(starts, screen, pin_index=rank)
+    _WORKER.update(opt=opt, rank=rank)
+
+
+def _worker_scan(task):
+    """One task of a worker process: a block of starts, lock-stepped among themselves."""
+    indices, starts, screen = task
+    return indices, _WORKER["opt"]._scan_local(starts, screen, pin_index=_WORKER["rank"])
 
 
 class Optimize:
@@ -273,6 +287,7 @@ class Optimize:
     workers = None
     workers_min_starts = 512
     starts_per_worker = 128
+    starts_per_task = 64          # a worker takes the start grid in blocks of this many searches, first come first served
 
     def __init__(self, args):
         self.args = args
@@ -436,16 +451,22 @@ class Optimize:
         from .. import _capi
         ndev = max(1, _capi.device_count()) if method == 'spawn' else 1
         first = self.dispersion.device if self.dispersion.device is not None else int(os.environ.get('OPTSTENCIL_DEVICE', 0))
+        # The cost of a search depends on where its start lies (whole rows of the start grid are rejected at once,
+        # others run a hundred iterates), so the grid is dealt in a fixed pseudo-random order, in blocks that the
+        # workers take first come first served.  Every search is independent and deterministic: the result does not
+        # depend on the dealing.
+        order = np.random.default_rng(len(starts)).permutation(len(starts))
+        per = max(1, min(self.starts_per_task, -(-len(starts) // workers)))
         tasks = []
-        for w in range(workers):                                # strided shares: cheap and expensive regions of the
-            idx = list(range(w, len(starts), workers))         # start grid are dealt evenly
-            tasks.append((self, idx, [starts[i] for i in idx], screen[idx], (first + w) % ndev, w))
+        for a in range(0, len(order), per):
+            idx = np.sort(order[a:a + per]).tolist()
+            tasks.append((idx, [starts[i] for i in idx], screen[idx]))
         results = [None] * len(starts)
-        with mp.get_context(method).Pool(workers) as pool:
-            for idx, part in pool.imap_unordered(_worker_scan, tasks):
+        with mp.get_context(method).Pool(workers, initializer=_worker_init, initargs=(self, first, ndev)) as pool:
+            for idx, part in pool.imap_unordered(_worker_scan, tasks, chunksize=1):
                 for i, r in zip(idx, part):
                     results[i] = r
-        self.scan_stats = dict(workers=workers, devices=min(ndev, workers))
+        self.scan_stats = dict(workers=workers, devices=min(ndev, workers), tasks=len(tasks))
         return results
 
     def optimize(self):

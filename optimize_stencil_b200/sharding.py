@@ -129,8 +129,9 @@ class ShardedObjective:
         return self.combine(gathered.view(self.world, 4, B))
 
 
-def device_evaluator(ctx, scan=False):
-    """evaluate_local for a CUDA `Context`: device tensors in, device tensor out, on torch's stream."""
+def device_evaluator(ctx, scan=False, fast=False):
+    """evaluate_local for a CUDA `Context`: device tensors in, device tensor out, on torch's stream.
+    scan / fast: the kernel variant (start-grid screening; the shorter series of throughput launches)."""
     import torch
 
     def run(block, x_begin, x_end, x_stride=1):
@@ -139,7 +140,7 @@ def device_evaluator(ctx, scan=False):
         out = torch.empty((4, block.shape[0]), dtype=torch.float64, device=block.device)
         ctx.objective_batch_device(block.data_ptr(), block.shape[0], out.data_ptr(), x_begin, x_end,
                                    stream=torch.cuda.current_stream(block.device).cuda_stream, x_stride=x_stride,
-                                   scan=scan)
+                                   scan=scan, fast=fast)
         return out
 
     return run

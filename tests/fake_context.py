@@ -54,7 +54,8 @@ class OracleContext:
                                  [g.kcomp[0].ravel()[sl]] + [c.ravel() for c in g.kcomp[1:]], g.Y, g.Z)
         return sub, (self.w if np.ndim(self.w) == 0 else self.w[sl])
 
-    def objective_batch(self, coeffs, x_begin=0, x_end=None, x_stride=1, seg_size=0, scan=False, shard="auto"):
+    def objective_batch(self, coeffs, x_begin=0, x_end=None, x_stride=1, seg_size=0, scan=False, shard="auto",
+                        fast=None):
         # segments, the screening variant and sharding change nothing in the results contract
         assert x_stride == 1, "the oracle-backed context evaluates contiguous slabs only"
         c = np.asarray(coeffs, dtype=float)

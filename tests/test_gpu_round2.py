@@ -119,15 +119,35 @@ def test_screening_variant_gives_the_same_results(sb):
     dxs = np.linspace(-1, 0.25, st_n + 2)[1:-1]
     co = np.stack([O.coefficients("StencilIsotropicDivFree3D", (t, x)) for t in dts for x in dxs])
     with ctx_from_grid(sb, O.Grid(3, 64)) as ctx:
-        plain = ctx.objective_batch(co)
+        plain = ctx.objective_batch(co, fast=True)                   # the screening variant uses the fast series
         assert np.mean(np.isnan(plain[0])) > 0.5                     # a screening-like batch indeed
         assert same_result(plain, ctx.objective_batch(co, scan=True))
         assert same_result(plain, ctx.objective_batch(co, scan="auto"))
         few = mixed_candidates(np.random.default_rng(2), 97)
-        assert same_result(ctx.objective_batch(few), ctx.objective_batch(few, scan=True))
+        assert same_result(ctx.objective_batch(few, fast=True), ctx.objective_batch(few, scan=True))
     with ctx_from_grid(sb, O.Grid(2, 90, 1.5)) as ctx:
         co2 = mixed_candidates(np.random.default_rng(3), 130, "StencilFree2D")
-        assert same_result(ctx.objective_batch(co2), ctx.objective_batch(co2, scan=True))
+        assert same_result(ctx.objective_batch(co2, fast=True), ctx.objective_batch(co2, scan=True))
+
+
+def test_fast_and_precise_series(sb):
+    """SB200_F_FAST trades 2.3e-16 for 3.7e-15 in asin: extrema and NaN flags identical, sums within 1e-14 of each
+    other and both inside the 1e-12 bar against the oracle; the automatic choice goes by segment size."""
+    grid = O.Grid(3, 40)
+    co = mixed_candidates(np.random.default_rng(17), 21)
+    with ctx_from_grid(sb, grid) as ctx:
+        precise, fast = ctx.objective_batch(co, fast=False), ctx.objective_batch(co, fast=True)
+        assert same_result(precise, ctx.objective_batch(co))          # small launch: precise by default
+        np.testing.assert_array_equal(precise[1], fast[1]); np.testing.assert_array_equal(precise[2], fast[2])
+        np.testing.assert_array_equal(precise[3] > 0, fast[3] > 0)
+        ok = ~np.isnan(precise[0])
+        assert np.max(relerr(fast[0][ok], precise[0][ok])) <= 1e-14
+        worst = {"precise": 0.0, "fast": 0.0}
+        for b in np.flatnonzero(ok):
+            S = O.device_contract(grid, co[b])[0]
+            worst["precise"] = max(worst["precise"], relerr(precise[0][b], S))
+            worst["fast"] = max(worst["fast"], relerr(fast[0][b], S))
+        assert worst["precise"] <= 2e-15 and worst["fast"] <= 1e-14, worst
 
 
 def test_combine_kernel_matches_the_host_combine(sb):
