@@ -241,7 +241,7 @@ int sb200_get_stream(const sb200_ctx* ctx, void** stream);
 int sb200_launch_count(const sb200_ctx* ctx, int64_t* launches);
 int sb200_last_batch_ms(const sb200_ctx* ctx, double* ms);
 
-/* Tile configuration override for experiments (0 = automatic): candidates per thread (1,2,4,8),
+/* Tile configuration override for experiments (0 = automatic): candidates per thread (1,2,3,4,8),
  * y-tile, x-tile.  Affects only speed and the (deterministic) summation order. */
 int sb200_set_tiling(sb200_ctx* ctx, int32_t cand_per_thread, int32_t tile_y, int32_t tile_x);
 

@@ -114,29 +114,38 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     const int ys = blockIdx.z * a.tile_y;
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
 
+    __shared__ long long s_probe[8];
     if (tid == 0) s_force = 0;
-    __syncthreads();
     if (tid < C) {
         const int seg = chunk / a.chunks_per_seg;
         const long long bend = (long long)(seg + 1) * a.seg_size;
         long long b = (long long)seg * a.seg_size + (long long)(chunk - seg * a.chunks_per_seg) * C + tid;
         if (b >= bend) b = bend - 1;  // pad the segment's last chunk with a copy; its results are not written
-        Cand& c = cand[tid];
-        load_candidate(c, a.coeffs + b * a.ncoef, a.ncoef);
-        // Are the guards of the header sufficient for this candidate?  (every test is false for NaNs)
+        load_candidate(cand[tid], a.coeffs + b * a.ncoef, a.ncoef);
+        s_probe[tid] = 0ll;
+    }
+    __syncthreads();
+    // Are the guards of the header sufficient for these candidates?  A lower bound of the grid maximum first: the
+    // largest sqrtarg on the 8 corners of the visited slab (the maximum sits on the far corner for Yee-like stencils,
+    // on an axis end for smoothed ones like Lehe's) -- one thread per (candidate, corner), the maximum taken on the
+    // raw bits (non-negative doubles order like integers; a negative value never beats the initial +0, a positive NaN
+    // beats everything and then fails the test below, which is the safe side).
+    for (int t = tid; t < 7 * C; t += blockDim.x) {
+        const int c = t / 7, q = t - 7 * c + 1;
+        const int xc = (q & 1) ? a.x_begin + (a.n_planes - 1) * a.x_stride : a.x_begin, yc = (q & 2) ? g.ny - 1 : 0, zc = (q & 4) ? g.nz - 1 : 0;
+        const double val = sqrtarg_exact_at<UNIT>(cand + c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc], g.sz2[zc],
+                                                  g.Y2, g.rY2, g.Z2, g.rZ2);
+        atomicMax(&s_probe[c], __double_as_longlong(val));
+    }
+    __syncthreads();
+    if (tid < C) {
+        const Cand& c = cand[tid];
         // Mbound: |cos| <= 1, |1 + 2 cos| <= 3, 0 <= s2 <= 1 for the reference's tables; tab_scale covers a
-        // caller who hands over anything else (it is 1 otherwise, NaN for NaN tables)
+        // caller who hands over anything else (it is 1 otherwise, NaN for NaN tables).  Every test is false for NaNs.
         const double mb = ((fabs(c.ax) + 3. * fabs(c.dlx) + fabs(c.bxy2) + fabs(c.bxz2)) +
                            (fabs(c.ay) + 3. * fabs(c.dly) + fabs(c.byx2) + fabs(c.byz2)) * rY +
                            (fabs(c.az) + 3. * fabs(c.dlz) + fabs(c.bzx2) + fabs(c.bzy2)) * rZ) * g.tab_scale;
-        // a lower bound of the grid maximum: the largest value on the 8 corners of the visited slab (the
-        // maximum sits on the far corner for Yee-like stencils, on an axis end for smoothed ones like Lehe's)
-        double probe = 0.;
-        for (int q = 1; q < 8; ++q) {
-            const int xc = (q & 1) ? a.x_begin + (a.n_planes - 1) * a.x_stride : a.x_begin, yc = (q & 2) ? g.ny - 1 : 0, zc = (q & 4) ? g.nz - 1 : 0;
-            probe = fmax(probe, sqrtarg_exact_at<UNIT>(&c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc],
-                                                       g.sz2[zc], g.Y2, g.rY2, g.Z2, g.rZ2));
-        }
+        const double probe = __longlong_as_double(s_probe[tid]);
         const bool sane = (mb <= 16. * probe) && (c.c2dt.x * mb <= 16777216.);
         if (!sane) atomicOr(&s_force, 1);
     }
@@ -154,6 +163,10 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         s_smax[c * blockDim.x + tid] = 0ll;
     }
 
+    // 0.375 (the cubic step of |k|'s square root) as an opaque register value: left to itself the compiler sometimes
+    // re-loads it from the constant bank in every iteration of the hot loop (2.5 % of the throughput)
+    // (built from a launch argument so that it cannot be re-materialised from the constant bank: a.P < 2^30 always)
+    const double c375 = __hiloint2double(0x3fd80000 + (a.P >> 30), 0);
     double* wrows = s_rows + (size_t)warp * ROWS * ROW;   // this warp's private table
     for (int i = ie - 1; i >= is; --i) {
         const int x = a.x_begin + i * a.x_stride;
@@ -237,7 +250,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                     if (WK != 0) w[u] = __ldg(wrow + (size_t)min(yy + u, nrows - 1) * g.nz);
                     // |k| (dispersion.py:350) to 1 ulp: its rounding enters (omega - k) like omega's own
                     // (2.8e-15) and far below it; the correctly rounded version costs 4 more instructions per row
-                    const double k = sqrt_approx(__dadd_rn(yk.y, kz2));
+                    const double k = sqrt_approx(__dadd_rn(yk.y, kz2), c375);
                     kr[u] = k;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -341,7 +354,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) z2[j] = __dmul_rn(W[j], 0.5);             // dt^2 A
                     // |v| <= sqrt(3)/2, or -1 + 2^-21 < v < -1/2, on every lane and chain: out of reach of every guard
-                    if (!dev_try_nosqrt<C, J, PREC>(v, hk, e, FULL) && !dev_try_low<C, J, true, PREC>(z2, v, kr, e, cand, FULL)) {
+                    if (!dev_try_nosqrt<C, J, PREC>(v, hk, e, FULL) && !dev_try_low<C, J, true, PREC>(z2, v, kr, e, cand, FULL, c375)) {
                         if (!redone) {
                             // v <= -1 + 2^-21 (sqrtarg may be negative or a negative NaN) or v within
                             // [1 - 2^-9 - 2^-12, 1 + 2^-12): the EXACT class needs the reference's bits there.
@@ -361,7 +374,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                                 for (int j = 0; j < J; ++j) A[j] = __dmul_rn(W[j], cand[j % C].ic2);   // read where s > 1 only
                             }
                         }
-                        dev_high_or_any<C, J, PREC>(A, z2, v, hk, kr, e, cand, FULL);
+                        dev_high_or_any<C, J, PREC>(A, z2, v, hk, kr, e, cand, FULL, c375);
                     }
                 }
 #pragma unroll

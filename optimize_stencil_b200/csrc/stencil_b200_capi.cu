@@ -285,7 +285,7 @@ static int create_impl(sb200_ctx* ctx, const sb200_grid_desc* d) {
     // experiment knobs (tools/sweep.py), read once: never on the launch path
     if (const char* ev = getenv("SB200_FORCE_C")) {
         const int v = atoi(ev);
-        if (v == 1 || v == 2 || v == 4 || v == 8) ctx->env_force_c = v;
+        if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8) ctx->env_force_c = v;
     }
     if (const char* ev = getenv("SB200_BLOCK_THREADS")) {
         const int v = atoi(ev);
@@ -393,7 +393,7 @@ extern "C" int sb200_set_weight(sb200_ctx* ctx, int32_t kind, const double* w, i
 
 extern "C" int sb200_set_tiling(sb200_ctx* ctx, int32_t c, int32_t ty, int32_t tx) {
     if (!ctx) return SB200_EINVAL;
-    if (!(c == 0 || c == 1 || c == 2 || c == 4 || c == 8)) return fail(ctx, SB200_EINVAL, "cand_per_thread must be 0,1,2,4,8");
+    if (!(c == 0 || c == 1 || c == 2 || c == 3 || c == 4 || c == 8)) return fail(ctx, SB200_EINVAL, "cand_per_thread must be 0,1,2,3,4,8");
     if (ty < 0 || tx < 0 || ty > 1024) return fail(ctx, SB200_EINVAL, "bad tile");
     ctx->force_c = c; ctx->force_ty = ty; ctx->force_tx = tx;
     return SB200_OK;
@@ -434,9 +434,12 @@ Plan make_plan(const sb200_ctx* ctx, const Request& r) {
     const long long B = r.seg;
     const int nxr = r.nplanes;
     Plan p;
-    // candidates per thread: 4 from B = 3 on (a padded fourth candidate costs less than the 2 x 2 layout's second
-    // pass over the tables: 52 vs 59 us for 3 x 128^3)
-    p.C = ctx->force_c ? ctx->force_c : (B >= 3 ? 4 : (B >= 2 ? 2 : 1));
+    // Candidates per thread: 4 chains in flight per thread saturate the FP64 pipe (8-cycle dependent issue, one
+    // instruction per 2 cycles).  Small batches take the C in {3, 4} that pads the last chunk least (an SLSQP
+    // iterate of a 2-parameter stencil is 3 rows: C = 4 would spend a quarter of the launch on a padded copy).
+    if (ctx->force_c) p.C = ctx->force_c;
+    else if (B >= 3) p.C = (B <= 64 && ((B + 2) / 3) * 3 < ((B + 3) / 4) * 4) ? 3 : 4;
+    else p.C = B >= 2 ? 2 : 1;
     if (ctx->env_force_c) p.C = ctx->env_force_c;
     const int tz_max = ctx->env_block_threads ? ctx->env_block_threads : 256;
     p.TZ = std::min(tz_max, ((g.nz + 31) / 32) * 32);
@@ -445,16 +448,20 @@ Plan make_plan(const sb200_ctx* ctx, const Request& r) {
     p.n_chunks = p.chunks_per_seg * r.nseg;
     p.TY = ctx->force_ty ? std::min(ctx->force_ty, g.ny) : g.ny;
     p.TX = ctx->force_tx ? std::min(ctx->force_tx, nxr) : nxr;
-    // Enough CTAs for ~16 waves of (2 CTAs x SMs) when the problem is that large; never below 8
-    // k-points of work per thread and candidate.
+    // Enough CTAs for ~16 waves of (2 CTAs x SMs) when the problem is that large -- the cost of a k-point depends
+    // on its class, many small CTAs balance that -- but never fewer than 128 rows per CTA: below that the
+    // prologue (candidate constants, corner probe, three barriers) and the epilogue cost more than the sweep
+    // (ncu of 32-row CTAs: 3.7 warps per issue slot stalled on barriers, FP64 pipe 38 % active).
     const long long target = (long long)ctx->sm_count * 2 * 16;
+    const int min_rows = 128;
     auto ctas = [&]() {
         return p.chunks_per_seg * p.n_ztiles * ((nxr + p.TX - 1) / p.TX) * ((g.ny + p.TY - 1) / p.TY);
     };
     if (!ctx->force_tx)
-        while (ctas() < target && p.TX > 1) p.TX = (p.TX + 1) / 2;
+        while (ctas() < target && p.TX > 1 && (long long)((p.TX + 1) / 2) * p.TY >= min_rows) p.TX = (p.TX + 1) / 2;
     if (!ctx->force_ty)
-        while (ctas() < target && p.TY > 32) p.TY = ((p.TY + 1) / 2 + 31) / 32 * 32;   // whole 32-row tiles
+        while (ctas() < target && p.TY > 32 && p.TX * (((p.TY + 1) / 2 + 31) / 32 * 32) >= min_rows)
+            p.TY = ((p.TY + 1) / 2 + 31) / 32 * 32;   // whole 32-row tiles
     p.n_xchunks = (nxr + p.TX - 1) / p.TX;
     p.n_ychunks = (g.ny + p.TY - 1) / p.TY;
     p.P = p.n_ztiles * p.n_xchunks * p.n_ychunks;
@@ -566,6 +573,7 @@ static int objective_device_impl(sb200_ctx* ctx, const double* d_coeffs, int64_t
     switch (p.C) {
         case 1: e = launch_objective<1>(ctx, p, a, r, st); break;
         case 2: e = launch_objective<2>(ctx, p, a, r, st); break;
+        case 3: e = launch_objective<3>(ctx, p, a, r, st); break;
         case 4: e = launch_objective<4>(ctx, p, a, r, st); break;
         default: e = launch_objective<8>(ctx, p, a, r, st); break;
     }

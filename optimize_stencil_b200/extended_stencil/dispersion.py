@@ -132,9 +132,13 @@ class Dispersion:
         """A facade for ONE search: same tables, stencil, weight and device context as this object, but its own
         parameters, result cache and finite-difference memo.  `submit(C) -> (S, Amin, Amax, nan)` replaces the
         direct launch (the lock-step server of optimize.py passes its own); None launches directly."""
-        self._context()                      # tables, context and weight upload happen once, on the parent
+        if submit is None:
+            self._context()                  # tables, context and weight upload happen once, on the parent
+        elif not self.init2_run:
+            self.init2()
         v = object.__new__(type(self))
         v.__dict__.update(self.__dict__)
+        v._w_scale = float(self._w) if np.ndim(self._w) == 0 else 1.0   # what _context() derives from the weight
         v._parameters = None
         v._coefficients = None
         v._cache = {}

@@ -13,11 +13,16 @@ constraints and options, optimize.py:136,142).  What changes is the data-paralle
                 launch, and the library guarantees a segment's results are bit-identical to a launch of its
                 own (include/stencil_b200.h, sb200_objective_batch_ex), so every search is bit-identical to
                 its stand-alone run (`lockstep = False`) whatever shares the launch;
-             3. a large start grid is additionally split over worker PROCESSES (`workers`), one GPU per
-                worker round-robin over the visible devices, which spreads SciPy's own per-iteration
-                Python time over the host cores; each worker runs step 2 on its share.  Starts are
-                independent and deterministic, so the result does not depend on the number of workers,
-                threads or GPUs.
+             3. for a large start grid SciPy's own per-iteration Python time (~0.1 ms per iterate, serial under
+                the interpreter lock) is what remains, so the searches are additionally dealt to worker PROCESSES
+                (`workers`).  The workers run SciPy only -- they never touch CUDA.  This process keeps the device
+                contexts (all visible GPUs as one device group) and serves them: every round it merges the blocks
+                of ALL workers into one segmented launch per dispersion object, sharded over the GPUs at segment
+                boundaries, and hands the slices back.  One Python process owns the devices (SURVEY.md 8e "process
+                model"); several processes sharing a GPU without MPS time-slice it and lose more than they gain
+                (measured: profiles/r02_scan_timing_1gpu.txt).  Starts are independent and deterministic and a
+                segment's bits do not depend on its company, so the result does not depend on the number of
+                workers, threads or GPUs.
              SLSQP is handed the forward differences it would take itself as `jac` callables and the
              constraint list stacked into one vector-valued constraint (`exact_fd_jac`: same points, same
              arithmetic, same rows -- the search is bit-identical, the Python overhead per iterate drops 3x).
@@ -29,6 +34,7 @@ import itertools
 import os
 import sys
 import threading
+import time
 
 import numpy as np
 import scipy.optimize as scop
@@ -148,7 +154,8 @@ class _LockStep:
 
     pin = os.environ.get('OPTSTENCIL_PIN', '1') != '0'
 
-    def __init__(self, pin_index=-1):
+    def __init__(self, evaluate, pin_index=-1):
+        self.evaluate = evaluate     # [(key, seg, C), ...] -> [(S, Amin, Amax, nan), ...]: the device work of one round
         self.pin_index = pin_index   # which of the allowed cores the search threads share (-1: the last one)
         self._waiting = []           # requests queued for the next round
         self._ready = []             # requests whose results are in (or start tokens), in wake-up order
@@ -156,10 +163,11 @@ class _LockStep:
         self.rounds = 0
         self.launches = 0
         self.rows = 0
+        self.device_seconds = 0.0    # wall time spent waiting for the device work over all rounds
 
-    def submitter(self, parent):
+    def submitter(self, key):
         def submit(C):
-            req = _Request(parent, C)
+            req = _Request(key, C)
             self._waiting.append(req)
             self._pass_baton()
             req.lock.acquire()                   # immediately, if this thread ran the round and is first in line
@@ -182,14 +190,15 @@ class _LockStep:
         try:
             groups = {}
             for req in batch:
-                groups.setdefault((id(req.parent), len(req.C)), []).append(req)
-            for reqs in groups.values():
-                parent, seg = reqs[0].parent, len(reqs[0].C)
-                C = np.concatenate([r.C for r in reqs]) if len(reqs) > 1 else reqs[0].C
-                ctx = parent._context(len(C) * parent._grid_points())
-                S, Amin, Amax, nan = ctx.objective_batch(C, seg_size=seg if len(reqs) > 1 else 0, fast=False)
+                groups.setdefault((req.parent, len(req.C)), []).append(req)
+            blocks = [(key, seg, np.concatenate([r.C for r in reqs]) if len(reqs) > 1 else reqs[0].C)
+                      for (key, seg), reqs in groups.items()]
+            t0 = time.perf_counter()
+            answers = self.evaluate(blocks)
+            self.device_seconds += time.perf_counter() - t0
+            for ((key, seg), reqs), (S, Amin, Amax, nan) in zip(groups.items(), answers):
                 self.launches += 1
-                self.rows += len(C)
+                self.rows += seg * len(reqs)
                 for n, r in enumerate(reqs):
                     sl = slice(n * seg, (n + 1) * seg)
                     r.result = (S[sl], Amin[sl], Amax[sl], nan[sl])
@@ -250,27 +259,35 @@ class _LockStep:
         return results
 
 
-_WORKER = {}
+def _launch_blocks(parents, blocks):
+    """The device work of one round: one segmented launch per (dispersion object, block length)."""
+    out = []
+    for key, seg, C in blocks:
+        parent = parents[key]
+        ctx = parent._context(len(C) * parent._grid_points())
+        out.append(ctx.objective_batch(C, seg_size=seg if len(C) > seg else 0, fast=False))
+    return out
 
 
-def _worker_init(opt, first_device, ndev):
-    """Once per worker process: the Optimize object (its Dispersion objects re-create their device contexts lazily,
-    like the reference's pickled objects re-run init2) on this worker's GPU -- workers are dealt round robin over
-    the visible devices."""
-    import multiprocessing as mp
-    ident = mp.current_process()._identity
-    rank = (ident[0] - 1) if ident else 0
-    device = (first_device + rank) % ndev
-    for d in (opt.dispersion, opt.dispersion_high):
-        d.device = device
-        d.devices = [device]
-    _WORKER.update(opt=opt, rank=rank)
-
-
-def _worker_scan(task):
-    """One task of a worker process: a block of starts, lock-stepped among themselves."""
-    indices, starts, screen = task
-    return indices, _WORKER["opt"]._scan_local(starts, screen, pin_index=_WORKER["rank"])
+def _scipy_worker(conn, opt, starts, screen, rank):
+    """Entry point of a worker process: its share of the searches, lock-stepped among themselves; every round's
+    blocks go to the process that owns the devices (`Optimize._serve`) and come back evaluated.  No CUDA here."""
+    try:
+        def remote(blocks):
+            conn.send(('eval', blocks))
+            answer = conn.recv()
+            if isinstance(answer, BaseException):
+                raise answer
+            return answer
+        out = opt._scan_local(starts, screen, pin_index=rank, evaluate=remote)
+        conn.send(('done', out, opt.scan_stats))
+    except BaseException as exc:
+        try:
+            conn.send(('error', exc))
+        except Exception:
+            conn.send(('error', RuntimeError(repr(exc))))
+    finally:
+        conn.close()
 
 
 class Optimize:
@@ -287,7 +304,6 @@ class Optimize:
     workers = None
     workers_min_starts = 512
     starts_per_worker = 128
-    starts_per_task = 64          # a worker takes the start grid in blocks of this many searches, first come first served
 
     def __init__(self, args):
         self.args = args
@@ -388,14 +404,18 @@ class Optimize:
         out = self.dispersion.evaluate_batch(P)
         return np.stack([out['dt_ok'], out['stencil_ok']], axis=1)
 
-    def _scan_local(self, starts, screen, pin_index=-1):
-        """Run the searches of `starts` in this process -> list of (x0, res, norm) in order."""
+    def _scan_local(self, starts, screen, pin_index=-1, evaluate=None):
+        """Run the searches of `starts` in this process -> list of (x0, res, norm) in order.  `evaluate`: where a
+        round's blocks are evaluated (None: on this process's device contexts)."""
         low, high = self.dispersion, self.dispersion_high
-        lockstep = self.lockstep and len(starts) >= 2
-        server = _LockStep(pin_index) if lockstep else None
-        sub_low = server.submitter(low) if lockstep else None
-        sub_high = sub_low if high is low else (server.submitter(high) if lockstep else None)
-        low._context(), high._context()                        # contexts and weights before any thread starts
+        lockstep = (self.lockstep and len(starts) >= 2) or evaluate is not None
+        parents = dict(low=low, high=high)
+        if evaluate is None:
+            low._context(), high._context()                    # contexts and weights before any thread starts
+            evaluate = lambda blocks: _launch_blocks(parents, blocks)   # noqa: E731
+        server = _LockStep(evaluate, pin_index) if lockstep else None
+        sub_low = server.submitter('low') if lockstep else None
+        sub_high = sub_low if high is low else (server.submitter('high') if lockstep else None)
 
         def job(s, sc):
             def run():
@@ -416,7 +436,8 @@ class Optimize:
                     for key, v in st.items():
                         d.stats[key] += v
         if lockstep:
-            self.scan_stats = dict(rounds=server.rounds, launches=server.launches, rows=server.rows)
+            self.scan_stats = dict(rounds=server.rounds, launches=server.launches, rows=server.rows,
+                                   device_seconds=round(server.device_seconds, 4))
         return [r for r, _, _ in done]
 
     def _worker_count(self, nstarts):
@@ -435,9 +456,66 @@ class Optimize:
                 cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
             except ImportError:
                 cores = os.cpu_count() or 1
-            w = min(cores, max(1, nstarts // self.starts_per_worker))
+            w = min(cores - 1, max(1, nstarts // self.starts_per_worker))    # one core serves the devices
         w = int(w)
         return w if w > 1 and nstarts >= 2 * w else 0
+
+    def _serve(self, conns):
+        """Serve the worker processes until all are done: every round, the blocks of all live workers are merged
+        per (dispersion object, block length) into one segmented launch (each block keeps its own segments, so
+        nothing depends on the merging), and every worker gets its slices back."""
+        parents = dict(low=self.dispersion, high=self.dispersion_high)
+        active = dict(enumerate(conns))
+        results, stats = {}, dict(rounds=0, launches=0, rows=0, device_seconds=0.0)
+        failure = None
+        while active:
+            pending = {}
+            for w, c in list(active.items()):
+                try:
+                    msg = c.recv()
+                except EOFError:
+                    msg = ('error', RuntimeError('worker %d died' % w))
+                if msg[0] == 'eval':
+                    pending[w] = msg[1]
+                else:
+                    del active[w]
+                    if msg[0] == 'done':
+                        results[w] = msg[1]
+                    elif failure is None:
+                        failure = msg[1]
+            if not pending:
+                continue
+            merged = {}
+            for w, blocks in pending.items():
+                for n, (key, seg, C) in enumerate(blocks):
+                    merged.setdefault((key, seg), []).append((w, n, C))
+            replies = {w: [None] * len(blocks) for w, blocks in pending.items()}
+            try:
+                if failure is not None:
+                    raise failure
+                t0 = time.perf_counter()
+                for (key, seg), items in merged.items():
+                    C = np.concatenate([c for _, _, c in items]) if len(items) > 1 else items[0][2]
+                    (S, Amin, Amax, nan), = _launch_blocks(parents, [(key, seg, C)])
+                    stats['launches'] += 1
+                    stats['rows'] += len(C)
+                    at = 0
+                    for w, n, c in items:
+                        sl = slice(at, at + len(c))
+                        replies[w][n] = (S[sl], Amin[sl], Amax[sl], nan[sl])
+                        at += len(c)
+                stats['rounds'] += 1
+                stats['device_seconds'] += time.perf_counter() - t0
+            except BaseException as exc:                       # fail every waiting worker; they report and exit
+                if failure is None:
+                    failure = exc
+                replies = {w: exc for w in pending}
+            for w in pending:
+                active[w].send(replies[w])
+        if failure is not None:
+            raise failure
+        stats['device_seconds'] = round(stats['device_seconds'], 4)
+        return results, stats
 
     def _scan(self, starts, screen):
         workers = self._worker_count(len(starts))
@@ -449,24 +527,42 @@ class Optimize:
             return self._scan_local(starts, screen)
         import multiprocessing as mp
         from .. import _capi
-        ndev = max(1, _capi.device_count()) if method == 'spawn' else 1
-        first = self.dispersion.device if self.dispersion.device is not None else int(os.environ.get('OPTSTENCIL_DEVICE', 0))
+        # The devices stay with this process; with more than one visible, the merged launches are sharded over all of
+        # them (segments are bit-identical whatever the number of devices).
+        if self.dispersion.devices is None and os.environ.get('OPTSTENCIL_DEVICES') is None and _capi.device_count() > 1:
+            for d in (self.dispersion, self.dispersion_high):
+                d.devices = 'all'
+        self.dispersion._context(), self.dispersion_high._context()
         # The cost of a search depends on where its start lies (whole rows of the start grid are rejected at once,
-        # others run a hundred iterates), so the grid is dealt in a fixed pseudo-random order, in blocks that the
-        # workers take first come first served.  Every search is independent and deterministic: the result does not
-        # depend on the dealing.
+        # others run a hundred iterates): deal the grid in a fixed pseudo-random order.  Every search is independent
+        # and deterministic, so the result does not depend on the dealing.
         order = np.random.default_rng(len(starts)).permutation(len(starts))
-        per = max(1, min(self.starts_per_task, -(-len(starts) // workers)))
-        tasks = []
-        for a in range(0, len(order), per):
-            idx = np.sort(order[a:a + per]).tolist()
-            tasks.append((idx, [starts[i] for i in idx], screen[idx]))
+        mpc = mp.get_context(method)
+        procs, conns, shares = [], [], []
+        t_start = time.perf_counter()
+        for w in range(workers):
+            idx = np.sort(order[w::workers]).tolist()
+            parent_end, child_end = mpc.Pipe()
+            p = mpc.Process(target=_scipy_worker, args=(child_end, self, [starts[i] for i in idx], screen[idx], w),
+                            daemon=True)
+            p.start()
+            child_end.close()
+            procs.append(p); conns.append(parent_end); shares.append(idx)
+        try:
+            by_worker, stats = self._serve(conns)
+        finally:
+            for c in conns:
+                c.close()
+            for p in procs:
+                p.join(timeout=30)
+                if p.is_alive():
+                    p.terminate()
         results = [None] * len(starts)
-        with mp.get_context(method).Pool(workers, initializer=_worker_init, initargs=(self, first, ndev)) as pool:
-            for idx, part in pool.imap_unordered(_worker_scan, tasks, chunksize=1):
-                for i, r in zip(idx, part):
-                    results[i] = r
-        self.scan_stats = dict(workers=workers, devices=min(ndev, workers), tasks=len(tasks))
+        for w, idx in enumerate(shares):
+            for i, r in zip(idx, by_worker[w]):
+                results[i] = r
+        self.scan_stats = dict(stats, workers=workers, devices=len(self.dispersion._context().devices),
+                               wall_seconds=round(time.perf_counter() - t_start, 3))
         return results
 
     def optimize(self):

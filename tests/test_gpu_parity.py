@@ -250,7 +250,7 @@ def test_argument_errors(sb):
         with pytest.raises(ValueError):
             ctx.objective_batch(np.zeros((2, 13)))
         with pytest.raises(sb.StencilB200Error):
-            ctx.set_tiling(3, 0, 0)
+            ctx.set_tiling(5, 0, 0)
     with pytest.raises(sb.StencilB200Error):
         sb.Context(3, [np.ones(4)] * 3, [np.zeros(4)] * 3, [np.zeros(4)] * 3, device=99)
 

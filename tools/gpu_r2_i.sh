@@ -1,0 +1,12 @@
+#!/bin/bash
+# round-2 GPU call I (8 GPUs): device-group tests, bench at N = 8 (incl. the k-slab sub-record), group bench, worker scan
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+NG=$(nvidia-smi -L | wc -l)
+nproc > gpurun_out/r2i_host.txt; free -g >> gpurun_out/r2i_host.txt
+timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -x -q --timeout 300 -k "group or devices or worker" > gpurun_out/r2i_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2i_pytest.log
+tail -3 gpurun_out/r2i_pytest.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $NG --steps 5 --warmup 3 > gpurun_out/r2i_bench_n$NG.json 2> gpurun_out/r2i_bench_n$NG.err; echo "bench rc=$?"
+head -c 200 gpurun_out/r2i_bench_n$NG.json; echo
+timeout 600 python tools/group_bench.py > gpurun_out/r2i_group_bench.txt 2>&1; cat gpurun_out/r2i_group_bench.txt
+timeout 600 python tools/scan_timing.py config3full > gpurun_out/r2i_scan_timing.txt 2>&1; cat gpurun_out/r2i_scan_timing.txt
