@@ -77,6 +77,123 @@ struct RowLayoutFA {
     static constexpr int ROWS = 32;
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Extrema-only sweep for a chunk whose candidates ALL violate the CFL limit at one of the 8 corners of the visited
+// slab (2 dt^2 sqrtarg >= 2.001 there, i.e. s > 1, i.e. omega is NaN at that k-point).  The sum of such a candidate is
+// NaN whatever the rest of the grid holds, so only min / max of sqrtarg remain to be found: the regrouped value and
+// the two filters per k-point (3 FP64 + 2 integer compares instead of ~20 FP64), the reference-order redo where a
+// lane asks -- the same exact values reach the extrema as in the full sweep, and S = NaN, nan > 0 are what the full
+// sweep returns too.  Start grids (optimize.py:118-134: most starts lie beyond the CFL limit) and the first rounds of
+// an SLSQP scan consist of such candidates.  A separate function (not inlined) so that its register allocation and
+// code motion stay out of the hot loop's.
+// ------------------------------------------------------------------------------------------------------------
+template <int C, bool UNIT>
+__device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArgs& a, const Cand* cand, const double* s_mb,
+                                                double* wrows, unsigned long long* s_umax, long long* s_smax, int ztile,
+                                                int is, int ie, int ys, int ye, bool force) {
+    constexpr int ROW = 2 + 2 * C, ROWS = 32;
+    constexpr int U = (C >= 4) ? 1 : 4 / C;
+    constexpr int J = U * C;
+    constexpr unsigned int FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
+    double Ts[C], tzys[C];
+    int thr[C];
+    // The minimum gets the mirror image of the maximum filter once the thread's running minimum is negative enough
+    // (|min| >= 2^-20 Mbound: two high-word units at the minimum then exceed the regrouping error 2^-47 Mbound by
+    // 2^7); until then every value that may be negative (2 dt^2 A' < 2^-21, sign-bit NaNs) asks for the exact one.
+    unsigned int thrneg[C];
+    bool negon[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { thr[c] = INT_MIN; thrneg[c] = 0x80000000u; negon[c] = false; }
+    for (int i = ie - 1; i >= is; --i) {
+        const int x = a.x_begin + i * a.x_stride;
+        const int zslice = (warp + i) % nwarps;
+        const int zraw = ztile * blockDim.x + zslice * 32 + lane;
+        if (__ballot_sync(FULL, zraw < g.nz) == 0u) continue;
+        const int z = min(zraw, g.nz - 1);                 // lanes past the end repeat the last point (extrema unaffected)
+        const double cz = g.cz[z], sz2 = g.sz2[z];
+        const double sz2r = __dmul_rn(sz2, rZ);
+        const double opz = __dadd_rn(1.0, __dmul_rn(2.0, cz));
+        const double cx = g.cx[x], sx2 = g.sx2[x];
+        const double opx = __dadd_rn(1.0, __dmul_rn(2.0, cx));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const double c2 = cand[c].c2dt.x;
+            const double tzx = __dmul_rn(cand[c].bxz2, cz);
+            const double tzzx = fma(cand[c].bzx2, cx, fma(cand[c].dlz, opz, cand[c].az));
+            tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
+            Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
+        }
+        for (int y1 = ye; y1 > ys; y1 -= ROWS) {
+            const int y0 = max(ys, y1 - ROWS);
+            const int nrows = y1 - y0;
+            __syncwarp();
+            {
+                const int y = min(y0 + lane, y1 - 1);
+                const double cy = g.cy[y];
+                const double opy = __dadd_rn(1.0, __dmul_rn(2.0, cy));
+                const double sy2r = __dmul_rn(g.sy2[y], rY);
+                double* row = wrows + lane * ROW;
+                *reinterpret_cast<double2*>(row) = make_double2(sy2r, 0.0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double c2 = cand[c].c2dt.x;
+                    const double axy = fma(cand[c].bxy2, cy, fma(cand[c].dlx, opx, cand[c].ax));
+                    const double ayx = fma(cand[c].byx2, cx, fma(cand[c].dly, opy, cand[c].ay));
+                    *reinterpret_cast<double2*>(row + 2 + 2 * c) =
+                        make_double2(__dmul_rn(c2, fma(axy, sx2, __dmul_rn(ayx, sy2r))), __dmul_rn(c2, __dmul_rn(cand[c].bzy2, cy)));
+                }
+            }
+            __syncwarp();
+            const int nit = (nrows + U - 1) / U;
+#pragma unroll 1
+            for (int yy = (nit - 1) * U; yy >= 0; yy -= U) {
+                bool need = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double* r = wrows + (size_t)min(yy + u, nrows - 1) * ROW;
+                    const double sy2r = r[0];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const double2 q = *reinterpret_cast<const double2*>(r + 2 + 2 * c);
+                        const int hw = __double2hiint(fma(tzys[c], sy2r, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c]))));
+                        // may reach the running maximum | may be (the most) negative, or a sign-bit NaN
+                        need = need || (hw >= thr[c]) || (negon[c] ? ((unsigned int)hw >= thrneg[c]) : (hw < 0x3ea00000));
+                    }
+                }
+                if (!__any_sync(FULL, need)) continue;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int y = y0 + min(yy + u, nrows - 1);
+                    const double cyr = g.cy[y], sy2 = g.sy2[y];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const double Ae = sqrtarg_exact_at<UNIT>(cand + c, cx, cyr, cz, sx2, sy2, sz2, g.Y2, g.rY2, g.Z2, g.rZ2);
+                        const long long bits = __double_as_longlong(Ae);
+                        long long* sm = s_smax + c * blockDim.x + tid;
+                        *sm = max(*sm, bits);
+                        if (bits < 0) {
+                            unsigned long long* um = s_umax + c * blockDim.x + tid;
+                            *um = max(*um, (unsigned long long)bits);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double wm = __dmul_rn(cand[c].c2dt.x, __longlong_as_double(s_smax[c * blockDim.x + tid]));
+                    thr[c] = force ? INT_MIN : max(__double2hiint(wm), 2) - 2;
+                    const double amin = __longlong_as_double((long long)s_umax[c * blockDim.x + tid]);   // +0 if none yet
+                    if (!force && amin <= -9.5367431640625e-07 * s_mb[c]) {                              // 2^-20 Mbound
+                        negon[c] = true;
+                        thrneg[c] = (unsigned int)__double2hiint(__dmul_rn(cand[c].c2dt.x, amin)) - 2u;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Shared memory: Cand[C] | rows | s_red | s_redu | s_umax | s_smax
 //
 // SCAN: the variant for start-grid screening (Optimize's first pass over the whole start grid, optimize.py:118-134
@@ -115,7 +232,9 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
 
     __shared__ long long s_probe[8];
-    if (tid == 0) s_force = 0;
+    __shared__ int s_alive, s_negcorner;
+    __shared__ double s_mb[8];
+    if (tid == 0) { s_force = 0; s_alive = 0; s_negcorner = 0; }
     if (tid < C) {
         const int seg = chunk / a.chunks_per_seg;
         const long long bend = (long long)(seg + 1) * a.seg_size;
@@ -136,6 +255,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const double val = sqrtarg_exact_at<UNIT>(cand + c, g.cx[xc], g.cy[yc], g.cz[zc], g.sx2[xc], g.sy2[yc], g.sz2[zc],
                                                   g.Y2, g.rY2, g.Z2, g.rZ2);
         atomicMax(&s_probe[c], __double_as_longlong(val));
+        if (val < 0.) atomicOr(&s_negcorner, 1 << c);   // sqrt of a negative sqrtarg: omega is NaN at that corner
     }
     __syncthreads();
     if (tid < C) {
@@ -148,6 +268,11 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         const double probe = __longlong_as_double(s_probe[tid]);
         const bool sane = (mb <= 16. * probe) && (c.c2dt.x * mb <= 16777216.);
         if (!sane) atomicOr(&s_force, 1);
+        // s > 1 at a corner for sure (2 dt^2 A >= 2.001; false for NaNs), or sqrtarg < 0 at a corner: omega is NaN
+        // there, so the sum is NaN whatever the rest of the grid holds
+        const bool dead = (__dmul_rn(c.c2dt.x, probe) >= 2.001) || ((s_negcorner >> tid) & 1);
+        if (!dead) atomicOr(&s_alive, 1);
+        s_mb[tid] = mb;
     }
     __syncthreads();
     const bool force = s_force != 0;   // CTA-uniform
@@ -161,6 +286,26 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
         S[c] = 0.; thr[c] = INT_MIN; dtc[c] = cand[c].dt;
         s_umax[c * blockDim.x + tid] = 0ull;   // own slots only: no barrier needed
         s_smax[c * blockDim.x + tid] = 0ll;
+    }
+
+    if (s_alive == 0) {
+        // every candidate of this chunk is beyond the CFL limit: extrema only, the sums are NaN (CTA-uniform branch)
+        int bz = blockIdx.z;
+        extrema_only_sweep<C, UNIT>(g, a, cand, s_mb, s_rows + (size_t)warp * ROWS * ROW, s_umax, s_smax, ztile, is, ie,
+                                    ys, min(bz * a.tile_y + a.tile_y, g.ny), force);
+        unsigned long long um[C];
+        long long sm[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            S[c] = __longlong_as_double(0x7ff8000000000000ll);
+            um[c] = s_umax[c * blockDim.x + tid];
+            sm[c] = s_smax[c * blockDim.x + tid];
+        }
+        const int seg_d = chunk / a.chunks_per_seg;
+        finish_candidates<C>(a, cand, S, um, sm, s_red, s_redu, chunk, ztile,
+                             (long long)seg_d * a.seg_size + (long long)(chunk - seg_d * a.chunks_per_seg) * C,
+                             (long long)(seg_d + 1) * a.seg_size);
+        return;
     }
 
     // 0.375 (the cubic step of |k|'s square root) as an opaque register value: left to itself the compiler sometimes

@@ -468,6 +468,8 @@ class Optimize:
         active = dict(enumerate(conns))
         results, stats = {}, dict(rounds=0, launches=0, rows=0, device_seconds=0.0)
         failure = None
+        round_log = [] if os.environ.get('OPTSTENCIL_ROUND_LOG') else None      # (round, rows, workers, device s, t)
+        t_serve = time.perf_counter()
         while active:
             pending = {}
             for w, c in list(active.items()):
@@ -506,6 +508,9 @@ class Optimize:
                         at += len(c)
                 stats['rounds'] += 1
                 stats['device_seconds'] += time.perf_counter() - t0
+                if round_log is not None:
+                    round_log.append((stats['rounds'], sum(len(c) for it in merged.values() for _, _, c in it),
+                                      len(pending), time.perf_counter() - t0, time.perf_counter() - t_serve))
             except BaseException as exc:                       # fail every waiting worker; they report and exit
                 if failure is None:
                     failure = exc
@@ -515,6 +520,11 @@ class Optimize:
         if failure is not None:
             raise failure
         stats['device_seconds'] = round(stats['device_seconds'], 4)
+        if round_log is not None:
+            with open(os.environ['OPTSTENCIL_ROUND_LOG'], 'w') as f:
+                f.write('# round rows live_workers device_seconds seconds_since_start\n')
+                for rec in round_log:
+                    f.write('%d %d %d %.6f %.4f\n' % rec)
         return results, stats
 
     def _scan(self, starts, screen):

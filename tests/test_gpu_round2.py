@@ -130,6 +130,45 @@ def test_screening_variant_gives_the_same_results(sb):
         assert same_result(ctx.objective_batch(co2, fast=True), ctx.objective_batch(co2, scan=True))
 
 
+@pytest.mark.parametrize("dim,N,Y,Z", [(3, 40, 1.0, 1.0), (3, 33, 1.3, 0.8), (2, 64, 1.0, 1.0), (2, 50, 1.25, 1.0)])
+def test_chunks_of_hopeless_candidates_take_the_extrema_only_sweep(sb, dim, N, Y, Z):
+    """Chunks whose candidates all have s > 1 or sqrtarg < 0 at a corner of the grid skip omega (the sum is NaN
+    anyway) and only look for min / max of sqrtarg: NaN sums, extrema bit for bit -- with the maximum filter, the
+    minimum filter (large negative regions) and its fallback (barely negative values) all in play."""
+    rng = np.random.default_rng(dim * 100 + N)
+    fam = "StencilFree3D" if dim == 3 else "StencilFree2D"
+    dof = len(O.parameter_names(fam))
+    rows = []
+    for _ in range(24):                                  # beyond the CFL limit: dt 1.1 .. 3
+        p = np.zeros(dof); p[0] = rng.uniform(1.1, 3.0); p[1:] = 0.02 * rng.standard_normal(dof - 1); rows.append(p)
+    for _ in range(24):                                  # large negative regions: wild betas / deltas
+        p = 0.6 * rng.standard_normal(dof); p[0] = rng.uniform(0.2, 0.9); rows.append(p)
+    for eps in (1e-3, 1e-9, 1e-14):                      # barely negative at the far corner: delta = (1 + eps) / 4 (Yee-like)
+        p = np.zeros(dof); p[0] = 0.3; p[-dim:] = 0.25 * (1 + eps); rows.append(p)
+    co = np.stack([O.coefficients(fam, p) for p in rows])
+    grid = O.Grid(dim, N, Y, Z)
+    with ctx_from_grid(sb, grid) as ctx:
+        for kw in (dict(), dict(seg_size=3), dict(fast=True)):
+            S, lo, hi, nan = ctx.objective_batch(co, **kw)
+            dead = 0
+            for b in range(len(co)):
+                Sr, amin, amax, nn = O.device_contract(grid, co[b])
+                assert bits(lo[b]) == bits(amin if amin < 0 else 0.0), (b, kw, lo[b], amin)
+                assert bits(hi[b]) == bits(max(amax, 0.0)), (b, kw, hi[b], amax)
+                assert (nan[b] > 0) == (nn > 0) and np.isnan(S[b]) == (nn > 0), (b, kw)
+                if nn == 0:
+                    assert relerr(S[b], Sr) <= 1e-12
+                dead += nn > 0
+            assert dead >= 40
+        # a hopeless candidate next to healthy ones in the same chunk: the full sweep serves both
+        mix = np.stack([co[0], O.coefficients(fam, XC[:dof]), co[30], O.coefficients(fam, XC[:dof] * 0.9)])
+        S, lo, hi, nan = ctx.objective_batch(mix)
+        for b in range(4):
+            Sr, amin, amax, nn = O.device_contract(grid, mix[b])
+            assert bits(hi[b]) == bits(max(amax, 0.0)) and bits(lo[b]) == bits(amin if amin < 0 else 0.0)
+            assert np.isnan(S[b]) == (nn > 0) and (nn > 0 or relerr(S[b], Sr) <= 1e-12)
+
+
 def test_fast_and_precise_series(sb):
     """SB200_F_FAST trades 2.3e-16 for 3.7e-15 in asin: extrema and NaN flags identical, sums within 1e-14 of each
     other and both inside the 1e-12 bar against the oracle; the automatic choice goes by segment size."""

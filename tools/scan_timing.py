@@ -30,7 +30,7 @@ CASES = {
                 ["sequential", "lockstep", "workers"]),
     "config3full": ("BASELINE.json configs[2]: --div-free --dim 3 --dtrange 0.6718 1.0 --N 64 on 128^3 (4096 searches)",
                     dict(dim=3, div_free=True, dtrange=[0.6718, 1.0], N=64, Ngrid_low=128, Ngrid_high=128),
-                    ["lockstep", "workers"] + (["sequential"] if os.environ.get("SCAN_TIMING_SEQUENTIAL") else [])),
+                    (["workers"] if os.environ.get("OPTSTENCIL_ROUND_LOG") else ["lockstep", "workers"]) + (["sequential"] if os.environ.get("SCAN_TIMING_SEQUENTIAL") else [])),
 }
 
 
