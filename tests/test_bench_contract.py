@@ -49,7 +49,7 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
 
 @pytest.mark.gpu
 def test_gpu_arm_runs_and_keeps_the_contract():
-    line = run_bench("--batch", "64", "--grid", "64", "--grid5", "96", "--steps", "2", "--warmup", "3")
+    line = run_bench("--batch", "64", "--grid", "64", "--grid5", "96", "--steps", "2", "--warmup", "3", "--quick-extras")
     assert BASE_KEYS | {"roofline", "clocks", "parity", "extra"} <= set(line)
     assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["gpu_launches"] == 2
     assert line["value"] > 0 and line["e2e"]["value"] > 0
