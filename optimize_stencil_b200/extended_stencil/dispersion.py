@@ -191,10 +191,11 @@ class Dispersion:
             return self._parent._context(evals)
         if not self.init2_run:
             self.init2()
-        if self._ctx is not None and evals >= self.auto_multi_evals and self.devices is None:
+        if self._ctx is not None and (self.devices is not None or evals >= self.auto_multi_evals):
             want = self._wanted_devices(evals)
-            if len(want) > len(self._ctx.devices):
-                self._ctx.close()            # never shrinks back: the extra contexts are paid for once
+            grow = len(want) > len(self._ctx.devices)         # automatic mode never shrinks back: the extra contexts
+            if grow or (self.devices is not None and list(want) != list(self._ctx.devices)):   # are paid for once
+                self._ctx.close()
                 self._ctx = None
         if self._ctx is None:
             cos, s2, kc = self._tables
