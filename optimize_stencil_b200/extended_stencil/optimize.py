@@ -30,6 +30,7 @@ constraints and options, optimize.py:136,142).  What changes is the data-paralle
 
 The printed lines keep the reference's format (optimize.py:71, 144, 191, 200-202).
 """
+import contextlib
 import itertools
 import os
 import sys
@@ -259,6 +260,21 @@ class _LockStep:
         return results
 
 
+@contextlib.contextmanager
+def _single_threaded_blas():
+    """SLSQP's linear algebra is a handful of tiny LAPACK calls per iterate.  Their bits depend on the number of BLAS
+    threads (measured: OMP_NUM_THREADS=1 against the default changes the printed optimum of a scan in the 10th
+    digit, with the objective held bit-identical), and dozens of worker processes with one BLAS thread pool each
+    oversubscribe the host.  One thread during a scan: the same trajectories on every machine and in every mode."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        yield
+        return
+    with threadpool_limits(limits=1):
+        yield
+
+
 def _launch_blocks(parents, blocks):
     """The device work of one round: one segmented launch per (dispersion object, block length)."""
     out = []
@@ -279,7 +295,8 @@ def _scipy_worker(conn, opt, starts, screen, rank):
             if isinstance(answer, BaseException):
                 raise answer
             return answer
-        out = opt._scan_local(starts, screen, pin_index=rank, evaluate=remote)
+        with _single_threaded_blas():
+            out = opt._scan_local(starts, screen, pin_index=rank, evaluate=remote)
         conn.send(('done', out, opt.scan_stats))
     except BaseException as exc:
         try:
@@ -378,7 +395,8 @@ class Optimize:
         return x0, res, high.norm(res.x)
 
     def _optimize_final(self, x0):
-        res = self._minimize(self.dispersion_high, self.constraints_high, x0)
+        with _single_threaded_blas():
+            res = self._minimize(self.dispersion_high, self.constraints_high, x0)
         print('x0={}, x={}, norm={}'.format(x0, res.x, res.fun))
         return res, res.fun
 
@@ -534,7 +552,8 @@ class Optimize:
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
             workers = 0
         if workers <= 1:
-            return self._scan_local(starts, screen)
+            with _single_threaded_blas():
+                return self._scan_local(starts, screen)
         import multiprocessing as mp
         from .. import _capi
         # The devices stay with this process; with more than one visible, the merged launches are sharded over all of
