@@ -266,12 +266,15 @@ def _single_threaded_blas():
     threads (measured: OMP_NUM_THREADS=1 against the default changes the printed optimum of a scan in the 10th
     digit, with the objective held bit-identical), and dozens of worker processes with one BLAS thread pool each
     oversubscribe the host.  One thread during a scan: the same trajectories on every machine and in every mode."""
+    if os.environ.get('OPTSTENCIL_BLAS_THREADS', '1') != '1':      # anything else: leave the BLAS thread pools alone
+        yield
+        return
     try:
         from threadpoolctl import threadpool_limits
     except ImportError:
         yield
         return
-    with threadpool_limits(limits=1):
+    with threadpool_limits(limits=1, user_api='blas'):
         yield
 
 
@@ -285,10 +288,13 @@ def _launch_blocks(parents, blocks):
     return out
 
 
-def _scipy_worker(conn, opt, starts, screen, rank):
+def _scipy_worker(conn, opt, rank):
     """Entry point of a worker process: its share of the searches, lock-stepped among themselves; every round's
-    blocks go to the process that owns the devices (`Optimize._serve`) and come back evaluated.  No CUDA here."""
+    blocks go to the process that owns the devices (`Optimize._serve`) and come back evaluated.  No CUDA here.
+    The share arrives over the pipe: the workers are started (and import NumPy / SciPy) while the owner still
+    creates its device contexts and screens the start grid."""
     try:
+        starts, screen = conn.recv()
         def remote(blocks):
             conn.send(('eval', blocks))
             answer = conn.recv()
@@ -545,39 +551,47 @@ class Optimize:
                     f.write('%d %d %d %.6f %.4f\n' % rec)
         return results, stats
 
-    def _scan(self, starts, screen):
-        workers = self._worker_count(len(starts))
+    def _start_workers(self, nstarts):
+        """Spawn the SciPy worker processes for a scan of `nstarts` searches (None: the scan stays in this process)."""
+        workers = self._worker_count(nstarts)
         method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')       # never fork a live CUDA context
         if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
             workers = 0
         if workers <= 1:
-            with _single_threaded_blas():
-                return self._scan_local(starts, screen)
+            return None
         import multiprocessing as mp
-        from .. import _capi
-        # The devices stay with this process; with more than one visible, the merged launches are sharded over all of
-        # them (segments are bit-identical whatever the number of devices).
-        if self.dispersion.devices is None and os.environ.get('OPTSTENCIL_DEVICES') is None and _capi.device_count() > 1:
-            for d in (self.dispersion, self.dispersion_high):
-                d.devices = 'all'
-        self.dispersion._context(), self.dispersion_high._context()
-        # The cost of a search depends on where its start lies (whole rows of the start grid are rejected at once,
-        # others run a hundred iterates): deal the grid in a fixed pseudo-random order.  Every search is independent
-        # and deterministic, so the result does not depend on the dealing.
-        order = np.random.default_rng(len(starts)).permutation(len(starts))
         mpc = mp.get_context(method)
-        procs, conns, shares = [], [], []
-        t_start = time.perf_counter()
+        procs, conns = [], []
         for w in range(workers):
-            idx = np.sort(order[w::workers]).tolist()
             parent_end, child_end = mpc.Pipe()
-            p = mpc.Process(target=_scipy_worker, args=(child_end, self, [starts[i] for i in idx], screen[idx], w),
-                            daemon=True)
+            p = mpc.Process(target=_scipy_worker, args=(child_end, self, w), daemon=True)
             p.start()
             child_end.close()
-            procs.append(p); conns.append(parent_end); shares.append(idx)
+            procs.append(p); conns.append(parent_end)
+        return procs, conns, time.perf_counter()
+
+    def _scan(self, starts, screen, pool=None):
+        if pool is None:
+            with _single_threaded_blas():
+                return self._scan_local(starts, screen)
+        from .. import _capi
+        procs, conns, t_start = pool
+        workers = len(procs)
         try:
+            # The devices stay with this process; with more than one visible, the merged launches are sharded over all
+            # of them (segments are bit-identical whatever the number of devices).
+            if self.dispersion.devices is None and os.environ.get('OPTSTENCIL_DEVICES') is None and _capi.device_count() > 1:
+                for d in (self.dispersion, self.dispersion_high):
+                    d.devices = 'all'
+            self.dispersion._context(), self.dispersion_high._context()
+            # The cost of a search depends on where its start lies (whole rows of the start grid are rejected at once,
+            # others run a hundred iterates): deal the grid in a fixed pseudo-random order.  Every search is
+            # independent and deterministic, so the result does not depend on the dealing.
+            order = np.random.default_rng(len(starts)).permutation(len(starts))
+            shares = [np.sort(order[w::workers]).tolist() for w in range(workers)]
+            for c, idx in zip(conns, shares):
+                c.send(([starts[i] for i in idx], screen[idx]))
             by_worker, stats = self._serve(conns)
         finally:
             for c in conns:
@@ -597,9 +611,16 @@ class Optimize:
     def optimize(self):
         """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
         starts = self.start_grid()
-        screen = self._prescreen(starts)
+        pool = self._start_workers(len(starts))     # first: they start up while this process screens the grid
+        try:
+            screen = self._prescreen(starts)
+        except BaseException:
+            if pool is not None:
+                for p in pool[0]:
+                    p.terminate()
+            raise
         best = None
-        for x0, res, norm in self._scan(starts, screen):
+        for x0, res, norm in self._scan(starts, screen, pool):
             print('x0={}, x={}, norm={}'.format(x0, res.x if res else None, norm))
             if best is None or norm < best[2]:
                 best = (x0, res, norm)
