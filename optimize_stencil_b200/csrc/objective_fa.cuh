@@ -89,24 +89,75 @@ struct RowLayoutFA {
 // ------------------------------------------------------------------------------------------------------------
 template <int C, bool UNIT>
 __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArgs& a, const Cand* cand, const double* s_mb,
-                                                double* wrows, unsigned long long* s_umax, long long* s_smax, int ztile,
-                                                int is, int ie, int ys, int ye, bool force) {
+                                                const double (*s_corner)[8], double* wrows, unsigned long long* s_umax,
+                                                long long* s_smax, int ztile, int is, int ie, int ys, int ye) {
     constexpr int ROW = 2 + 2 * C, ROWS = 32;
     constexpr int U = (C >= 4) ? 1 : 4 / C;
-    constexpr int J = U * C;
     constexpr unsigned int FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
     double Ts[C], tzys[C];
-    int thr[C];
-    // The minimum gets the mirror image of the maximum filter once the thread's running minimum is negative enough
-    // (|min| >= 2^-20 Mbound: two high-word units at the minimum then exceed the regrouping error 2^-47 Mbound by
-    // 2^7); until then every value that may be negative (2 dt^2 A' < 2^-21, sign-bit NaNs) asks for the exact one.
+    // The maximum filter compares doubles here: "2 dt^2 A' may reach the running maximum" is !(A' < thr) with
+    // thr = (1 - 2^-20) * 2 dt^2 * (running exact maximum) once that maximum is sizeable against the regrouping error
+    // (2^-47 Mbound; asked for: maximum >= 2^-20 Mbound, and 2 dt^2 Mbound <= 2^24 as in the full sweep).  Until then
+    // every value that may be positive asks for the exact one: thr = -2^-40 * 2 dt^2 Mbound, so that the all-negative
+    // part of the grid of a stencil gone negative (78 % of it for the iterates an SLSQP line search throws at the
+    // delta = 1/4 bound) is passed over without a single exact evaluation.  Unlike the full sweep's CTA-wide `force`
+    // this is decided as the sweep goes: such a stencil has no positive corner to vouch for its maximum beforehand,
+    // but the first positive values it meets do.  -inf = "always ask" (NaN or absurdly scaled coefficients).
+    double thr[C];
+    // The minimum gets the mirror image once the thread's running minimum is negative enough (|min| >= 2^-20 Mbound:
+    // two high-word units at the minimum then exceed the regrouping error by 2^7); until then every value that may be
+    // negative (2 dt^2 A' < 2^-21, sign-bit NaNs) asks for the exact one.
     unsigned int thrneg[C];
     bool negon[C];
+    const double minus_inf = __longlong_as_double(0xfff0000000000000ll);
 #pragma unroll
-    for (int c = 0; c < C; ++c) { thr[c] = INT_MIN; thrneg[c] = 0x80000000u; negon[c] = false; }
-    for (int i = ie - 1; i >= is; --i) {
+    for (int c = 0; c < C; ++c) { thr[c] = minus_inf; thrneg[c] = 0x80000000u; negon[c] = false; }
+    auto refresh = [&]() {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const double c2 = cand[c].c2dt.x, tiny = 9.5367431640625e-07 * s_mb[c];          // 2^-20 Mbound
+            const bool scale_ok = c2 * s_mb[c] <= 16777216.;                                  // false for NaNs
+            const double amax = __longlong_as_double(s_smax[c * blockDim.x + tid]);
+            const double wm = __dmul_rn(c2, amax);
+            thr[c] = !scale_ok ? minus_inf
+                               : (amax >= tiny ? fma(-9.5367431640625e-07, wm, wm) : -9.094947017729282e-13 * (c2 * s_mb[c]));
+            const double amin = __longlong_as_double((long long)s_umax[c * blockDim.x + tid]);   // +0 if none yet
+            if (scale_ok && amin <= -tiny) {
+                negon[c] = true;
+                thrneg[c] = (unsigned int)__double2hiint(__dmul_rn(c2, amin)) - 2u;
+            }
+        }
+    };
+    // The 8 corners of the visited slab are grid points, evaluated exactly in the prologue: they seed every thread's
+    // running extrema (for a Yee-like stencil the far corner IS the maximum, for a stencil gone negative it is the
+    // minimum), and the corner with the largest value tells from which end to walk x and y -- the filters fire while
+    // the values still rise along the walk, so the walk starts where sqrtarg is largest.
+    int qmax = 0;
+    {
+        double best = 0.;
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+            if (s_corner[0][q] > best) { best = s_corner[0][q]; qmax = q; }
+    }
+    const bool xup = !(qmax & 1), yup = !(qmax & 2);          // the largest corner sits at the low end: walk upwards
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        long long sm = 0ll;
+        unsigned long long um = 0ull;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            const long long bits = __double_as_longlong(s_corner[c][q]);
+            sm = max(sm, bits);
+            if (bits < 0) um = max(um, (unsigned long long)bits);
+        }
+        s_smax[c * blockDim.x + tid] = sm;
+        s_umax[c * blockDim.x + tid] = um;
+    }
+    refresh();
+    for (int ii = 0; ii < ie - is; ++ii) {
+        const int i = xup ? is + ii : ie - 1 - ii;
         const int x = a.x_begin + i * a.x_stride;
         const int zslice = (warp + i) % nwarps;
         const int zraw = ztile * blockDim.x + zslice * 32 + lane;
@@ -125,8 +176,9 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
             tzys[c] = __dmul_rn(c2, __dmul_rn(cand[c].byz2, cz));
             Ts[c] = __dmul_rn(c2, fma(tzx, sx2, __dmul_rn(tzzx, sz2r)));
         }
-        for (int y1 = ye; y1 > ys; y1 -= ROWS) {
-            const int y0 = max(ys, y1 - ROWS);
+        for (int t = 0; t * ROWS < ye - ys; ++t) {
+            const int y0 = yup ? ys + t * ROWS : max(ys, ye - (t + 1) * ROWS);
+            const int y1 = yup ? min(ye, y0 + ROWS) : ye - t * ROWS;
             const int nrows = y1 - y0;
             __syncwarp();
             {
@@ -148,7 +200,8 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
             __syncwarp();
             const int nit = (nrows + U - 1) / U;
 #pragma unroll 1
-            for (int yy = (nit - 1) * U; yy >= 0; yy -= U) {
+            for (int it = 0; it < nit; ++it) {
+                const int yy = (yup ? it : nit - 1 - it) * U;
                 bool need = false;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -157,9 +210,10 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const double2 q = *reinterpret_cast<const double2*>(r + 2 + 2 * c);
-                        const int hw = __double2hiint(fma(tzys[c], sy2r, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c]))));
-                        // may reach the running maximum | may be (the most) negative, or a sign-bit NaN
-                        need = need || (hw >= thr[c]) || (negon[c] ? ((unsigned int)hw >= thrneg[c]) : (hw < 0x3ea00000));
+                        const double wv = fma(tzys[c], sy2r, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c])));
+                        const int hw = __double2hiint(wv);
+                        // may reach the running maximum (or is a NaN) | may be (the most) negative, or a sign-bit NaN
+                        need = need || !(wv < thr[c]) || (negon[c] ? ((unsigned int)hw >= thrneg[c]) : (hw < 0x3ea00000));
                     }
                 }
                 if (!__any_sync(FULL, need)) continue;
@@ -179,16 +233,7 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
                         }
                     }
                 }
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const double wm = __dmul_rn(cand[c].c2dt.x, __longlong_as_double(s_smax[c * blockDim.x + tid]));
-                    thr[c] = force ? INT_MIN : max(__double2hiint(wm), 2) - 2;
-                    const double amin = __longlong_as_double((long long)s_umax[c * blockDim.x + tid]);   // +0 if none yet
-                    if (!force && amin <= -9.5367431640625e-07 * s_mb[c]) {                              // 2^-20 Mbound
-                        negon[c] = true;
-                        thrneg[c] = (unsigned int)__double2hiint(__dmul_rn(cand[c].c2dt.x, amin)) - 2u;
-                    }
-                }
+                refresh();
             }
         }
     }
@@ -234,6 +279,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     __shared__ long long s_probe[8];
     __shared__ int s_alive, s_negcorner;
     __shared__ double s_mb[8];
+    __shared__ double s_corner[8][8];        // [candidate][corner q]: sqrtarg on the corners of the visited slab
     if (tid == 0) { s_force = 0; s_alive = 0; s_negcorner = 0; }
     if (tid < C) {
         const int seg = chunk / a.chunks_per_seg;
@@ -256,6 +302,7 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
                                                   g.Y2, g.rY2, g.Z2, g.rZ2);
         atomicMax(&s_probe[c], __double_as_longlong(val));
         if (val < 0.) atomicOr(&s_negcorner, 1 << c);   // sqrt of a negative sqrtarg: omega is NaN at that corner
+        if (SCAN || PREC == 1) s_corner[c][q] = val;    // (only the variants with the extrema-only path read them)
     }
     __syncthreads();
     if (tid < C) {
@@ -294,8 +341,8 @@ objective_kernel_fa(const GridDev g, const BatchArgs a) {
     if ((SCAN || PREC == 1) && s_alive == 0) {
         // every candidate of this chunk is beyond the CFL limit: extrema only, the sums are NaN (CTA-uniform branch)
         int bz = blockIdx.z;
-        extrema_only_sweep<C, UNIT>(g, a, cand, s_mb, s_rows + (size_t)warp * ROWS * ROW, s_umax, s_smax, ztile, is, ie,
-                                    ys, min(bz * a.tile_y + a.tile_y, g.ny), force);
+        extrema_only_sweep<C, UNIT>(g, a, cand, s_mb, s_corner, s_rows + (size_t)warp * ROWS * ROW, s_umax, s_smax, ztile,
+                                    is, ie, ys, min(bz * a.tile_y + a.tile_y, g.ny));
         unsigned long long um[C];
         long long sm[C];
 #pragma unroll

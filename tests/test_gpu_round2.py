@@ -145,7 +145,17 @@ def test_chunks_of_hopeless_candidates_take_the_extrema_only_sweep(sb, dim, N, Y
         p = 0.6 * rng.standard_normal(dof); p[0] = rng.uniform(0.2, 0.9); rows.append(p)
     for eps in (1e-3, 1e-9, 1e-14):                      # barely negative at the far corner: delta = (1 + eps) / 4 (Yee-like)
         p = np.zeros(dof); p[0] = 0.3; p[-dim:] = 0.25 * (1 + eps); rows.append(p)
-    co = np.stack([O.coefficients(fam, p) for p in rows])
+    co = [O.coefficients(fam, p) for p in rows]
+    if dim == 3:
+        # what an SLSQP line search throws at the delta = 1/4 bound of the div-free isotropic family (config 3): corners
+        # 0 / +-1e-12 / -2 / -6, four fifths of the grid negative, the maximum 1/4 on a surface inside the grid
+        for dt, d in ((0.6718, 0.25), (0.6718000001, 0.25), (0.7, 0.25 - 1e-9), (0.6718, 0.26), (0.9, 0.3), (0.5, 0.2501)):
+            co.append(O.coefficients("StencilIsotropicDivFree3D", [dt, d]))
+    while True:                                          # sqrtarg = 0 everywhere (dt = 0: not an s > 1 case); also pads
+        co.append(np.zeros(len(co[0])))                  # the batch to whole segments of 3
+        if len(co) % 3 == 0:
+            break
+    co = np.stack(co)
     grid = O.Grid(dim, N, Y, Z)
     with ctx_from_grid(sb, grid) as ctx:
         for kw in (dict(), dict(seg_size=3), dict(fast=True)):
@@ -167,6 +177,10 @@ def test_chunks_of_hopeless_candidates_take_the_extrema_only_sweep(sb, dim, N, Y
             Sr, amin, amax, nn = O.device_contract(grid, mix[b])
             assert bits(hi[b]) == bits(max(amax, 0.0)) and bits(lo[b]) == bits(amin if amin < 0 else 0.0)
             assert np.isnan(S[b]) == (nn > 0) and (nn > 0 or relerr(S[b], Sr) <= 1e-12)
+        # omega = (2/dt) asin(dt sqrt(A)) is even in dt, bit for bit (dispersion.py:191): so is the device's
+        flipped = mix.copy()
+        flipped[:, 0] = -flipped[:, 0]
+        assert same_result(ctx.objective_batch(flipped), (S, lo, hi, nan))
 
 
 def test_fast_and_precise_series(sb):
