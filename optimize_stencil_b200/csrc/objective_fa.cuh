@@ -92,42 +92,38 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
                                                 const double (*s_corner)[8], double* wrows, unsigned long long* s_umax,
                                                 long long* s_smax, int ztile, int is, int ie, int ys, int ye) {
     constexpr int ROW = 2 + 2 * C, ROWS = 32;
-    constexpr int U = (C >= 4) ? 1 : 4 / C;
+    constexpr int U = (C >= 8) ? 1 : 8 / C;      // rows per iteration: 6 to 8 independent chains in flight per thread
     constexpr unsigned int FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
     const double rY = UNIT ? 1.0 : g.rY2, rZ = UNIT ? 1.0 : g.rZ2;
     double Ts[C], tzys[C];
-    // The maximum filter compares doubles here: "2 dt^2 A' may reach the running maximum" is !(A' < thr) with
-    // thr = (1 - 2^-20) * 2 dt^2 * (running exact maximum) once that maximum is sizeable against the regrouping error
-    // (2^-47 Mbound; asked for: maximum >= 2^-20 Mbound, and 2 dt^2 Mbound <= 2^24 as in the full sweep).  Until then
-    // every value that may be positive asks for the exact one: thr = -2^-40 * 2 dt^2 Mbound, so that the all-negative
-    // part of the grid of a stencil gone negative (78 % of it for the iterates an SLSQP line search throws at the
-    // delta = 1/4 bound) is passed over without a single exact evaluation.  Unlike the full sweep's CTA-wide `force`
-    // this is decided as the sweep goes: such a stencil has no positive corner to vouch for its maximum beforehand,
-    // but the first positive values it meets do.  -inf = "always ask" (NaN or absurdly scaled coefficients).
-    double thr[C];
-    // The minimum gets the mirror image once the thread's running minimum is negative enough (|min| >= 2^-20 Mbound:
-    // two high-word units at the minimum then exceed the regrouping error by 2^7); until then every value that may be
-    // negative (2 dt^2 A' < 2^-21, sign-bit NaNs) asks for the exact one.
-    unsigned int thrneg[C];
-    bool negon[C];
+    // Both filters compare doubles here (two DSETPs per point, chained on one predicate: no branches, no integer
+    // work): a point is passed over iff  tmin < 2 dt^2 A' < tmax,  anything else -- NaNs included -- asks for the exact
+    // value.  With M the regrouping error bound 2^-47 Mbound, and 2 dt^2 Mbound <= 2^24 as in the full sweep:
+    //   tmax = (1 - 2^-20) * 2 dt^2 * (running exact maximum) once that maximum is >= 2^-20 Mbound (the slack then
+    //          exceeds the error by 2^7); until then every value that may be positive asks: tmax = -2^-40 * 2 dt^2
+    //          Mbound, so that the all-negative part of the grid of a stencil gone negative (78 % of it for the
+    //          iterates an SLSQP line search throws at the delta = 1/4 bound) is passed over without a single exact
+    //          evaluation.  Unlike the full sweep's CTA-wide `force` this is decided as the sweep goes: such a stencil
+    //          has no positive corner to vouch for its maximum beforehand, but the first positive values it meets do.
+    //   tmin = (1 - 2^-20) * 2 dt^2 * (running exact minimum) once that minimum is <= -2^-20 Mbound; until then every
+    //          value that may be negative asks: tmin = 2^-21 (the error is below 2^-23 on this scale).
+    // -inf / +inf = "always ask" (NaN or absurdly scaled coefficients).
+    double tmax[C], tmin[C];
     const double minus_inf = __longlong_as_double(0xfff0000000000000ll);
 #pragma unroll
-    for (int c = 0; c < C; ++c) { thr[c] = minus_inf; thrneg[c] = 0x80000000u; negon[c] = false; }
+    for (int c = 0; c < C; ++c) { tmax[c] = minus_inf; tmin[c] = -minus_inf; }
     auto refresh = [&]() {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const double c2 = cand[c].c2dt.x, tiny = 9.5367431640625e-07 * s_mb[c];          // 2^-20 Mbound
             const bool scale_ok = c2 * s_mb[c] <= 16777216.;                                  // false for NaNs
             const double amax = __longlong_as_double(s_smax[c * blockDim.x + tid]);
-            const double wm = __dmul_rn(c2, amax);
-            thr[c] = !scale_ok ? minus_inf
-                               : (amax >= tiny ? fma(-9.5367431640625e-07, wm, wm) : -9.094947017729282e-13 * (c2 * s_mb[c]));
             const double amin = __longlong_as_double((long long)s_umax[c * blockDim.x + tid]);   // +0 if none yet
-            if (scale_ok && amin <= -tiny) {
-                negon[c] = true;
-                thrneg[c] = (unsigned int)__double2hiint(__dmul_rn(c2, amin)) - 2u;
-            }
+            const double wmax = __dmul_rn(c2, amax), wmin = __dmul_rn(c2, amin);
+            tmax[c] = !scale_ok ? minus_inf
+                                : (amax >= tiny ? fma(-9.5367431640625e-07, wmax, wmax) : -9.094947017729282e-13 * (c2 * s_mb[c]));
+            tmin[c] = !scale_ok ? -minus_inf : (amin <= -tiny ? fma(-9.5367431640625e-07, wmin, wmin) : 4.76837158203125e-07);
         }
     };
     // The 8 corners of the visited slab are grid points, evaluated exactly in the prologue: they seed every thread's
@@ -202,7 +198,7 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
 #pragma unroll 1
             for (int it = 0; it < nit; ++it) {
                 const int yy = (yup ? it : nit - 1 - it) * U;
-                bool need = false;
+                bool pass = true;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double* r = wrows + (size_t)min(yy + u, nrows - 1) * ROW;
@@ -211,11 +207,10 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
                     for (int c = 0; c < C; ++c) {
                         const double2 q = *reinterpret_cast<const double2*>(r + 2 + 2 * c);
                         const double wv = fma(tzys[c], sy2r, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c])));
-                        const int hw = __double2hiint(wv);
-                        // may reach the running maximum (or is a NaN) | may be (the most) negative, or a sign-bit NaN
-                        need = need || !(wv < thr[c]) || (negon[c] ? ((unsigned int)hw >= thrneg[c]) : (hw < 0x3ea00000));
+                        pass = pass && (wv < tmax[c]) && (wv > tmin[c]);
                     }
                 }
+                const bool need = !pass;
                 if (!__any_sync(FULL, need)) continue;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {

@@ -325,6 +325,7 @@ class Optimize:
     # Worker processes for large start grids: None = automatic (none below `workers_min_starts` searches, else one
     # per `starts_per_worker` searches up to the physical cores), 0 = never, N = exactly N.
     workers = None
+    serve_all_at_once = os.environ.get('OPTSTENCIL_SERVE', 'ready') == 'all'
     workers_min_starts = 512
     starts_per_worker = 128
 
@@ -485,18 +486,24 @@ class Optimize:
         return w if w > 1 and nstarts >= 2 * w else 0
 
     def _serve(self, conns):
-        """Serve the worker processes until all are done: every round, the blocks of all live workers are merged
-        per (dispersion object, block length) into one segmented launch (each block keeps its own segments, so
-        nothing depends on the merging), and every worker gets its slices back."""
+        """Serve the worker processes until all are done: every round, the blocks of the workers that are waiting are
+        merged per (dispersion object, block length) into one segmented launch (each block keeps its own segments,
+        so nothing depends on the merging or on who shares a launch), and every worker gets its slices back."""
         parents = dict(low=self.dispersion, high=self.dispersion_high)
         active = dict(enumerate(conns))
         results, stats = {}, dict(rounds=0, launches=0, rows=0, device_seconds=0.0)
         failure = None
         round_log = [] if os.environ.get('OPTSTENCIL_ROUND_LOG') else None      # (round, rows, workers, device s, t)
         t_serve = time.perf_counter()
+        from multiprocessing.connection import wait
+        owner = {id(c): w for w, c in active.items()}
         while active:
             pending = {}
-            for w, c in list(active.items()):
+            # Whoever has handed in its blocks is served at once: while the devices work on them, the other workers
+            # run their SLSQP steps, and what arrives meanwhile forms the next launch (a busy device batches by
+            # itself, an idle one answers immediately).  `serve_all_at_once` waits for every live worker instead.
+            ready = active if self.serve_all_at_once else {owner[id(c)]: c for c in wait(list(active.values()))}
+            for w, c in sorted(ready.items()):
                 try:
                     msg = c.recv()
                 except EOFError:
