@@ -6,6 +6,7 @@ below raise `StencilB200Error` -- loudly, by design.
 """
 import ctypes
 import os
+import sys
 
 import numpy as np
 
@@ -54,6 +55,19 @@ class _BatchOpts(ctypes.Structure):
 
 
 _lib = None
+_cuda_touched = False
+
+
+def cuda_touched():
+    """Has this process called into the CUDA runtime yet (through this library, or through an imported torch)?  A
+    process that has must not be forked (Optimize starts its SciPy workers by fork only while this is False)."""
+    if _cuda_touched:
+        return True
+    torch = sys.modules.get("torch")
+    try:
+        return bool(torch is not None and torch.cuda.is_initialized())
+    except Exception:
+        return True
 
 
 def load_library():
@@ -126,7 +140,9 @@ def _f64(a, shape=None):
 
 
 def device_count():
+    global _cuda_touched
     lib = load_library()
+    _cuda_touched = True
     n = ctypes.c_int32(0)
     if lib.sb200_device_count(ctypes.byref(n)) != 0:
         return 0
@@ -134,7 +150,9 @@ def device_count():
 
 
 def fp64_peak_tflops(device=0, seconds=0.25):
+    global _cuda_touched
     lib = load_library()
+    _cuda_touched = True
     out = ctypes.c_double(0.0)
     rc = lib.sb200_fp64_peak(device, seconds, ctypes.byref(out))
     if rc != 0:
@@ -166,7 +184,9 @@ class Context:
     """
 
     def __init__(self, dim, cos_kappa, s2, kcomp, Y=1.0, Z=1.0, device=0, devices=None):
+        global _cuda_touched
         self._lib = load_library()
+        _cuda_touched = True
         self._h = ctypes.c_void_p(None)
         self._grp = ctypes.c_void_p(None)
         self.dim = int(dim)

@@ -11,6 +11,7 @@ import numpy as np
 
 from . import extended_stencil
 from .extended_stencil import Dispersion2D, Dispersion3D, Optimize, get_stencil, weight_functions
+from .extended_stencil.optimize import _trace
 
 _AXES = ("x", "y", "z")
 _BETAS = ("xy", "xz", "yx", "yz", "zx", "zy")
@@ -95,6 +96,7 @@ def main_optimize(argv=None):
     print('Arguments are:', args)
     print('Starting Optimization.')
     opt = Optimize(args)
+    _trace('Optimize object built')
     x, fmin = opt.optimize()
     coefficients = opt.stencil.coefficients(x)
     print('\nOptimization finished. Results:\n')
@@ -118,6 +120,7 @@ def main_optimize(argv=None):
     print("end:stencil\n")
     if args.write_omega:
         opt.omega_output(args.write_omega, x)
+    _trace('output written')
     return 0
 
 

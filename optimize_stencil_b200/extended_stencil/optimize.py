@@ -132,6 +132,15 @@ class _stacked_constraints:
 SLSQP_OPTIONS = dict(disp=False, iprint=2)
 
 
+_T0 = time.perf_counter()
+
+
+def _trace(what):
+    """OPTSTENCIL_TRACE=1: stage times on stderr (seconds since this module was imported)."""
+    if os.environ.get('OPTSTENCIL_TRACE'):
+        sys.stderr.write('[optimize %8.3f s] %s\n' % (time.perf_counter() - _T0, what))
+
+
 class _Request:
     __slots__ = ("parent", "C", "result", "error", "lock")
 
@@ -561,7 +570,13 @@ class Optimize:
     def _start_workers(self, nstarts):
         """Spawn the SciPy worker processes for a scan of `nstarts` searches (None: the scan stays in this process)."""
         workers = self._worker_count(nstarts)
-        method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')       # never fork a live CUDA context
+        # Never fork a process that has called into CUDA.  One that has not -- the command-line tool gets here before
+        # its first device call -- forks: the workers are there at once instead of after 0.8 s of interpreter start
+        # and NumPy / SciPy imports each.  They never touch CUDA themselves.
+        from .. import _capi
+        method = os.environ.get('OPTSTENCIL_START_METHOD')
+        if method is None:
+            method = 'fork' if hasattr(os, 'fork') and not _capi.cuda_touched() else 'spawn'
         if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
             workers = 0
@@ -576,6 +591,7 @@ class Optimize:
             p.start()
             child_end.close()
             procs.append(p); conns.append(parent_end)
+        self._start_method = method
         return procs, conns, time.perf_counter()
 
     def _scan(self, starts, screen, pool=None):
@@ -592,6 +608,7 @@ class Optimize:
                 for d in (self.dispersion, self.dispersion_high):
                     d.devices = 'all'
             self.dispersion._context(), self.dispersion_high._context()
+            _trace('device contexts ready')
             # The cost of a search depends on where its start lies (whole rows of the start grid are rejected at once,
             # others run a hundred iterates): deal the grid in a fixed pseudo-random order.  Every search is
             # independent and deterministic, so the result does not depend on the dealing.
@@ -599,7 +616,9 @@ class Optimize:
             shares = [np.sort(order[w::workers]).tolist() for w in range(workers)]
             for c, idx in zip(conns, shares):
                 c.send(([starts[i] for i in idx], screen[idx]))
+            _trace('shares dealt')
             by_worker, stats = self._serve(conns)
+            _trace('workers served')
         finally:
             for c in conns:
                 c.close()
@@ -607,20 +626,25 @@ class Optimize:
                 p.join(timeout=30)
                 if p.is_alive():
                     p.terminate()
+            _trace('workers joined')
         results = [None] * len(starts)
         for w, idx in enumerate(shares):
             for i, r in zip(idx, by_worker[w]):
                 results[i] = r
-        self.scan_stats = dict(stats, workers=workers, devices=len(self.dispersion._context().devices),
+        self.scan_stats = dict(stats, workers=workers, start_method=self._start_method,
+                               devices=len(self.dispersion._context().devices),
                                wall_seconds=round(time.perf_counter() - t_start, 3))
         return results
 
     def optimize(self):
         """Scan the grid of starting values, keep the best local optimum, polish it at high resolution."""
         starts = self.start_grid()
+        _trace('start grid of %d points' % len(starts))
         pool = self._start_workers(len(starts))     # first: they start up while this process screens the grid
+        _trace('workers started' if pool else 'no workers')
         try:
             screen = self._prescreen(starts)
+            _trace('start grid screened')
         except BaseException:
             if pool is not None:
                 for p in pool[0]:
@@ -632,12 +656,14 @@ class Optimize:
             if best is None or norm < best[2]:
                 best = (x0, res, norm)
         sys.stdout.flush()
+        _trace('scan done: %s' % (self.scan_stats,))
         bestx0, bestres, bestnorm = best
         if self.args.Ngrid_high != self.args.Ngrid_low:
             print()
             print('using this result as starting point for high-res optimization:')
             print('x0={},x={}, norm={}'.format(bestx0, bestres.x, bestnorm))
             bestres, bestnorm = self._optimize_final(bestres.x)
+        _trace('final optimisation done')
         return bestres.x, bestnorm
 
     def omega_output(self, fname, x):

@@ -1,8 +1,12 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-python tools/config3_scan.py > gpurun_out/r2z_c3.txt 2>&1; rc=$?; tail -2 gpurun_out/r2z_c3.txt | cut -c1-200
-if [ $rc -eq 0 ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:objective_kernel --launch-skip 1 -c 1 -o gpurun_out/r2z_c3scan -f python tools/config3_scan.py > gpurun_out/r2z_ncu.log 2>&1
-  tail -3 gpurun_out/r2z_ncu.log
-fi
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_smoke.log 2>&1; tail -2 gpurun_out/r2z_smoke.log
+time python bench.py --steps 5 --warmup 3 > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/r2z_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2z_bench.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d.get('parity'))
+for k,v in d.get('extra',{}).items(): print(k, json.dumps(v)[:400])
+PY
