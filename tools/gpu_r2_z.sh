@@ -1,12 +1,4 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_smoke.log 2>&1; tail -2 gpurun_out/r2z_smoke.log
-time python bench.py --steps 5 --warmup 3 > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; echo "bench rc=$?"
-tail -3 gpurun_out/r2z_bench.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2z_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d.get('parity'))
-for k,v in d.get('extra',{}).items(): print(k, json.dumps(v)[:400])
-PY
+python tools/small_bench.py > gpurun_out/r2z_small.txt 2>&1; cat gpurun_out/r2z_small.txt

@@ -40,20 +40,23 @@ if "seg3d" in cases:
     N = 128
     x = np.linspace(0, np.pi, N)
     ctx = sb.Context(3, [np.cos(x)] * 3, [0.5 * (1 - np.cos(x))] * 3, [x] * 3)
-    for nseg in (64, 512, 4096):
-        P = np.array([0.6718, -0.0135]) + 1e-3 * rng.standard_normal((3 * nseg, 2))
-        co = StencilIsotropicDivFree3D().coefficients_batch(P)
-        t = timed(ctx, co, seg_size=3, fast=False)
-        print("3-D 128^3, %5d segments of 3 (an SLSQP round of %d searches): %8.3f ms  %7.1f G evals/s"
-              % (nseg, nseg, 1e3 * t, 3 * nseg * N ** 3 / t / 1e9), flush=True)
-        t = timed(ctx, co, fast=False)
-        print("3-D 128^3, the same %5d rows as ONE batch:                     %8.3f ms  %7.1f G evals/s"
-              % (3 * nseg, 1e3 * t, 3 * nseg * N ** 3 / t / 1e9), flush=True)
+    # live iterates: 2 dt^2 max(sqrtarg) = 1.89 (the CFL limit of delta_x = -0.0135 is dt = 0.5356); hopeless ones: the
+    # same stencil at the lower end of config 3's dt range, 2 dt^2 max(sqrtarg) = 3.15 -- the extrema-only sweep
+    for (dt0, what) in ((0.52, "live"), (0.6718, "hopeless")):
+        for nseg in (64, 512, 4096):
+            P = np.array([dt0, -0.0135]) + 1e-3 * rng.standard_normal((3 * nseg, 2))
+            co = StencilIsotropicDivFree3D().coefficients_batch(P)
+            t = timed(ctx, co, seg_size=3, fast=False)
+            print("3-D 128^3, %5d segments of 3 (an SLSQP round of %d %s searches): %8.3f ms  %7.1f G evals/s"
+                  % (nseg, nseg, what, 1e3 * t, 3 * nseg * N ** 3 / t / 1e9), flush=True)
+            t = timed(ctx, co, fast=False)
+            print("3-D 128^3, the same %5d rows as ONE batch:                     %8.3f ms  %7.1f G evals/s"
+                  % (3 * nseg, 1e3 * t, 3 * nseg * N ** 3 / t / 1e9), flush=True)
 if "single3d" in cases:
     N = 128
     x = np.linspace(0, np.pi, N)
     ctx = sb.Context(3, [np.cos(x)] * 3, [0.5 * (1 - np.cos(x))] * 3, [x] * 3)
-    co = StencilIsotropicDivFree3D().coefficients_batch(np.array([0.6718, -0.0135]) + 1e-3 * rng.standard_normal((3, 2)))
+    co = StencilIsotropicDivFree3D().coefficients_batch(np.array([0.52, -0.0135]) + 1e-3 * rng.standard_normal((3, 2)))
     ctx.objective_batch(co)
     t0 = time.perf_counter()
     for _ in range(200):
