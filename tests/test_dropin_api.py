@@ -4,7 +4,10 @@ Every test runs twice: on CPU with the oracle-backed context injected (tests/fak
 check the host logic, and under `-m gpu` against the real CUDA context.  Expected
 values come from the fixtures the unmodified reference produced (oracle/make_golden.py).
 """
+import os
 import pickle
+import subprocess
+import sys
 import types
 
 import numpy as np
@@ -459,6 +462,41 @@ def test_worker_processes_give_the_same_answer(monkeypatch, capsys):
     x2, f2 = es.Optimize(default_args(workers=2, singlecore=False, **over)).optimize()
     assert f1 == f2 and np.array_equal(x1, x2)
     assert capsys.readouterr().out.count("x0=") == 2 * 16
+
+
+def test_serving_order_does_not_matter(monkeypatch, capsys):
+    """Workers are served as they become ready (default) or all at once per round (OPTSTENCIL_SERVE=all): segments make
+    the composition of a launch irrelevant, so every printed line is the same; the stage trace goes to stderr."""
+    fake_context.install(monkeypatch)
+    monkeypatch.setenv("OPTSTENCIL_START_METHOD", "fork")
+    monkeypatch.setenv("OPTSTENCIL_TRACE", "1")
+    from optimize_stencil_b200 import extended_stencil as es
+    over = dict(div_free=True, dtrange=[0.6718, 1.0], Ngrid_low=24, Ngrid_high=24, N=4, workers=3, singlecore=False)
+    outs, stats = [], []
+    for at_once in (False, True):
+        monkeypatch.setattr(es.Optimize, "serve_all_at_once", at_once)
+        opt = es.Optimize(default_args(**over))
+        x, f = opt.optimize()
+        cap = capsys.readouterr()
+        outs.append((cap.out, tuple(x), f))
+        stats.append(opt.scan_stats)
+        assert "workers served" in cap.err and "scan done" in cap.err
+    assert outs[0] == outs[1]
+    assert stats[0]["rows"] == stats[1]["rows"] and stats[0]["start_method"] == "fork"
+    assert stats[0]["launches"] >= stats[1]["launches"]          # at most as much merging as with a barrier per round
+
+
+def test_fork_only_before_the_first_cuda_call():
+    """`_capi.cuda_touched()` is what `Optimize._start_workers` goes by: False in a fresh process, True after the first
+    call that reaches the CUDA runtime (here: the device count, which works without a GPU)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from optimize_stencil_b200 import _capi\n"
+            "assert not _capi.cuda_touched()\n"
+            "_capi.device_count()\n"
+            "assert _capi.cuda_touched()\n"
+            "print('ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
 
 
 @pytest.mark.gpu
