@@ -570,13 +570,15 @@ class Optimize:
     def _start_workers(self, nstarts):
         """Spawn the SciPy worker processes for a scan of `nstarts` searches (None: the scan stays in this process)."""
         workers = self._worker_count(nstarts)
-        # Never fork a process that has called into CUDA.  One that has not -- the command-line tool gets here before
-        # its first device call -- forks: the workers are there at once instead of after 0.8 s of interpreter start
-        # and NumPy / SciPy imports each.  They never touch CUDA themselves.
+        # Spawned by default: a fresh interpreter per worker costs 0.2 s of the scan's wall time (they start while this
+        # process creates its CUDA context) and is safe whatever threads the caller already runs.  Forking
+        # (OPTSTENCIL_START_METHOD=fork) is honoured only while this process has not called into CUDA; the workers
+        # never touch CUDA themselves.
         from .. import _capi
-        method = os.environ.get('OPTSTENCIL_START_METHOD')
-        if method is None:
-            method = 'fork' if hasattr(os, 'fork') and not _capi.cuda_touched() else 'spawn'
+        method = os.environ.get('OPTSTENCIL_START_METHOD', 'spawn')
+        if method == 'fork' and (not hasattr(os, 'fork') or _capi.cuda_touched()):
+            print('optimize: not forking a process that has called into CUDA; spawning the workers instead')
+            method = 'spawn'
         if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
             workers = 0

@@ -468,9 +468,10 @@ def test_serving_order_does_not_matter(monkeypatch, capsys):
     """Workers are served as they become ready (default) or all at once per round (OPTSTENCIL_SERVE=all): segments make
     the composition of a launch irrelevant, so every printed line is the same; the stage trace goes to stderr."""
     fake_context.install(monkeypatch)
+    from optimize_stencil_b200 import _capi, extended_stencil as es
     monkeypatch.setenv("OPTSTENCIL_START_METHOD", "fork")
+    monkeypatch.setattr(_capi, "cuda_touched", lambda: False)     # earlier tests of this process asked for the device count
     monkeypatch.setenv("OPTSTENCIL_TRACE", "1")
-    from optimize_stencil_b200 import extended_stencil as es
     over = dict(div_free=True, dtrange=[0.6718, 1.0], Ngrid_low=24, Ngrid_high=24, N=4, workers=3, singlecore=False)
     outs, stats = [], []
     for at_once in (False, True):
@@ -484,6 +485,14 @@ def test_serving_order_does_not_matter(monkeypatch, capsys):
     assert outs[0] == outs[1]
     assert stats[0]["rows"] == stats[1]["rows"] and stats[0]["start_method"] == "fork"
     assert stats[0]["launches"] >= stats[1]["launches"]          # at most as much merging as with a barrier per round
+    # a process that has called into CUDA is not forked, whatever the environment says: the workers are spawned
+    monkeypatch.setattr(_capi, "cuda_touched", lambda: True)
+    opt = es.Optimize(default_args(**over))
+    x, f = opt.optimize()
+    cap = capsys.readouterr()
+    assert opt.scan_stats["start_method"] == "spawn" and "spawning the workers instead" in cap.out
+    assert (cap.out.replace("optimize: not forking a process that has called into CUDA; spawning the workers instead\n", ""),
+            tuple(x), f) == outs[0]
 
 
 def test_fork_only_before_the_first_cuda_call():
@@ -501,7 +510,7 @@ def test_fork_only_before_the_first_cuda_call():
 
 @pytest.mark.gpu
 def test_worker_processes_on_the_gpu(capsys):
-    """Same with real spawned workers, each creating its own CUDA context on the shared GPU."""
+    """Same with real spawned workers (SciPy only) served by this process, which owns the device."""
     from optimize_stencil_b200 import extended_stencil as es
     over = dict(div_free=True, dtrange=[0.6718, 1.0], Ngrid_low=30, Ngrid_high=30, N=4)
     x1, f1 = es.Optimize(default_args(**over)).optimize()
