@@ -43,6 +43,8 @@
  *       dim 2:  dt, alphax, alphay, betaxy, betayx, deltax, deltay                     (7 doubles)
  *       dim 3:  dt, alphax, alphay, alphaz, betaxy, betaxz, betayx, betayz, betazx,
  *               betazy, deltax, deltay, deltaz                                         (13 doubles)
+ *     omega = (2/dt) asin(dt sqrt(sqrtarg)) is even in dt bit for bit, so the device works with |dt|; dt = 0 gives
+ *     S = NaN and nan > 0 (0/0 at every k-point, as in the reference).
  *   - the grid is C-ordered with the first axis (x) slowest, like the reference's arrays.
  *   - results are the UN-GATED grid reductions; the reference's gating (stencil_ok < 0, dt_ok < 0,
  *     the 1e6 sentinel, the ValueErrors) is applied by the caller from (S, Amin, Amax, nan),
