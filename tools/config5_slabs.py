@@ -46,19 +46,19 @@ if world > 1:
     dist.barrier()
 dt = (time.perf_counter() - t0) / K
 res = out.cpu().numpy()[:, 0]
-x0, x1 = sh.my_planes()
-# parity of this rank's slab on two thin sub-slabs
+x0, x1, xs = sh.my_planes()            # this rank's planes: x0, x0 + xs, ... below x1
+# parity of this rank's share on two thin sub-lists of its planes
 ok = True
-for a, b in ((x0, min(x0 + 2, x1)), (max(x1 - 2, x0), x1)):
-    got = ctx.objective_batch(co, a, b)
-    Sr, amin, amax, nn = O.device_contract(O.Grid(3, N, xslab=(a, b)), co[0])
+for a, b in ((x0, min(x0 + 2 * xs, x1)), (max(x0 + ((x1 - 1 - x0) // xs - 1) * xs, x0), x1)):
+    got = ctx.objective_batch(co, a, b, xs)
+    Sr, amin, amax, nn = O.device_contract(O.Grid(3, N, xslab=(a, b, xs)), co[0])
     ok &= abs(got[0][0] - Sr) <= 1e-12 * abs(Sr) and got[2][0] == max(amax, 0.0)
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 if world > 1:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("config 5: N=%d^3 single candidate, %d rank(s), slabs of %d planes: %.3f ms per objective, %.1f G evals/s, "
-          "S=%.15g Amax=%.17g, slab parity vs oracle: %s" % (N, world, x1 - x0, dt * 1e3, float(N) ** 3 / dt / 1e9,
+          "S=%.15g Amax=%.17g, slab parity vs oracle: %s" % (N, world, len(range(x0, x1, xs)), dt * 1e3, float(N) ** 3 / dt / 1e9,
                                                              res[0], res[2], "ok" if flag.item() == 1.0 else "FAILED"))
 if world > 1:
     dist.destroy_process_group()
