@@ -372,8 +372,13 @@ def run_gpu_arm(a):
     pin_in = torch.empty(bmax, dtype=torch.float64).pin_memory() if world > 1 else None
     pin_out = torch.empty(world * bmax, dtype=torch.float64).pin_memory() if world > 1 else None
 
+    parts = dict(norm_batch=0.0, kernel=0.0)   # where the end-to-end step goes (seconds, summed over the timed steps)
+
     def e2e_step():
+        t = time.perf_counter()
         mine = disp.norm_batch(params[lo:hi])
+        parts["norm_batch"] += time.perf_counter() - t
+        parts["kernel"] += ctx.last_batch_ms * 1e-3
         if world == 1:
             return mine
         pin_in[:hi - lo] = torch.from_numpy(mine)
@@ -388,11 +393,16 @@ def run_gpu_arm(a):
     for _ in range(max(1, min(a.warmup, 2))):
         e2e_step()
     env.barrier()
+    parts.update(norm_batch=0.0, kernel=0.0)
     t0 = time.perf_counter()
     for s in range(a.steps):
         norms = e2e_step()
+    t_loop = time.perf_counter() - t0
     env.barrier()
-    e2e_s = env.max_over_ranks([time.perf_counter() - t0])[0]
+    e2e_s, nb_s, k_s, loop_s = env.max_over_ranks([time.perf_counter() - t0, parts["norm_batch"], parts["kernel"], t_loop])
+    e2e_parts = dict(norm_batch_ms=nb_s / a.steps * 1e3, of_which_kernel_ms=k_s / a.steps * 1e3,
+                     gather_and_host_ms=(loop_s - nb_s) / a.steps * 1e3,
+                     note="max over ranks, per step; the all-gather waits for the slowest rank's kernel")
     e2e_value = evals_per_step * a.steps / e2e_s
     scale = (np.pi / (N - 1)) ** 3
     # same candidates, same kernel; the shard-local tiling may differ from the device path's in the last bits
@@ -454,7 +464,7 @@ def run_gpu_arm(a):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=dev_ms_max / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f64", data="synthetic", config=config_dict(a), clocks=clocks,
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, parts=e2e_parts,
                          api="Dispersion3D.norm_batch(params) on host arrays, all %d rows (every rank its shard: "
                              "Stencil.coefficients_batch -> sb200_objective_batch (ctypes C-ABI, pinned H2D / D2H) -> "
                              "the reference's gate)%s; byte counts are sums over the ranks" %

@@ -64,6 +64,8 @@ class Dispersion:
     devices = None             # None: automatic (one device; every visible device once a batch is large enough to
                                # pay for the extra contexts, or what $OPTSTENCIL_DEVICES says: "all", "0,1,..."),
                                # 'all', or a sequence of CUDA ordinals
+    throughput_evals = float(2 ** 32)   # evaluations in ONE evaluate_batch call from which it is a throughput launch (fast
+                                        # series, no cache warming) even if its rows would fit the per-point cache
     auto_multi_evals = float(2 ** 36)   # k-point x candidate evaluations in ONE batch from which `devices = None`
                                         # brings up the other GPUs (~0.1 s of one B200; a context costs ~0.3 s once)
     fd_prefetch = True         # evaluate x + h*e_i alongside every cache miss (see module docstring)
@@ -333,7 +335,11 @@ class Dispersion:
         if not np.any(ok):
             return out
         Pok = np.ascontiguousarray(P[ok])
-        if len(Pok) * 4 <= self.cache_size and self._submit is None:
+        # Small batches warm the per-point cache of the scalar API (precise series, like every search launch).  A batch
+        # that is seconds of CPU work per row is a throughput launch whatever its row count: 512 rows on 512^3 are
+        # what one of eight ranks gets of the 4096-row benchmark batch.
+        if (len(Pok) * 4 <= self.cache_size and self._submit is None
+                and len(Pok) * self._grid_points() < self.throughput_evals):
             S, Amin, Amax, nan, C = self._raw_batch(Pok)
         else:
             C = self.stencil.coefficients_batch(Pok)
