@@ -1000,8 +1000,15 @@ extern "C" int sb200_group_create(sb200_group** out, const sb200_grid_desc* desc
     };
     {
         std::vector<std::thread> pool;
-        for (size_t i = 1; i < G; ++i) pool.emplace_back(create_one, i);
-        create_one(0);
+        std::vector<size_t> inline_jobs(1, 0);
+        for (size_t i = 1; i < G; ++i) {
+            try {
+                pool.emplace_back(create_one, i);
+            } catch (...) {               // no thread to be had: this one is created by the caller's thread
+                inline_jobs.push_back(i);
+            }
+        }
+        for (size_t i : inline_jobs) create_one(i);
         for (std::thread& t : pool) t.join();
     }
     for (size_t i = 0; i < G; ++i)
