@@ -317,7 +317,13 @@ extern "C" int sb200_create(sb200_ctx** out, const sb200_grid_desc* d) {
     if (rc) return rc;
     sb200_ctx* ctx = new (std::nothrow) sb200_ctx();
     if (!ctx) return fail(nullptr, SB200_ENOMEM, "out of host memory");
-    rc = create_impl(ctx, d);
+    try {                                   // std::vector / std::thread inside: no exception may cross the C boundary
+        rc = create_impl(ctx, d);
+    } catch (const std::bad_alloc&) {
+        rc = fail(ctx, SB200_ENOMEM, "out of host memory");
+    } catch (...) {
+        rc = fail(ctx, SB200_ECUDA, "unexpected C++ exception while creating the context");
+    }
     if (rc != SB200_OK) {
         snprintf(g_create_error, sizeof g_create_error, "%s", ctx->err);
         sb200_destroy(ctx);
@@ -964,7 +970,35 @@ extern "C" void sb200_group_destroy(sb200_group* grp) {
     delete grp;
 }
 
+static int group_create_impl(sb200_group** out, const sb200_grid_desc* desc, const int32_t* devices, int32_t ndevices);
+static int group_objective_batch_impl(sb200_group* grp, const double* coeffs, int64_t B, int32_t shard,
+                                      const sb200_batch_opts* opts, double* S, double* Amin, double* Amax, int64_t* nan,
+                                      int32_t* used);
+
+// The group functions use std::vector and std::thread: no exception may cross the C boundary.
 extern "C" int sb200_group_create(sb200_group** out, const sb200_grid_desc* desc, const int32_t* devices, int32_t ndevices) {
+    try {
+        return group_create_impl(out, desc, devices, ndevices);
+    } catch (const std::bad_alloc&) {
+        return gfail(nullptr, SB200_ENOMEM, "out of host memory");
+    } catch (...) {
+        return gfail(nullptr, SB200_ECUDA, "unexpected C++ exception while creating the device group");
+    }
+}
+
+extern "C" int sb200_group_objective_batch(sb200_group* grp, const double* coeffs, int64_t B, int32_t shard,
+                                           const sb200_batch_opts* opts, double* S, double* Amin, double* Amax,
+                                           int64_t* nan, int32_t* used) {
+    try {
+        return group_objective_batch_impl(grp, coeffs, B, shard, opts, S, Amin, Amax, nan, used);
+    } catch (const std::bad_alloc&) {
+        return gfail(grp, SB200_ENOMEM, "out of host memory");
+    } catch (...) {
+        return gfail(grp, SB200_ECUDA, "unexpected C++ exception in the device group");
+    }
+}
+
+static int group_create_impl(sb200_group** out, const sb200_grid_desc* desc, const int32_t* devices, int32_t ndevices) {
     if (!out) return gfail(nullptr, SB200_EINVAL, "out is NULL");
     *out = nullptr;
     int rc = check_desc(desc, g_group_error);
@@ -1048,9 +1082,9 @@ extern "C" int sb200_group_set_weight(sb200_group* grp, int32_t kind, const doub
     return SB200_OK;
 }
 
-extern "C" int sb200_group_objective_batch(sb200_group* grp, const double* coeffs, int64_t B, int32_t shard,
-                                           const sb200_batch_opts* opts, double* S, double* Amin, double* Amax,
-                                           int64_t* nan, int32_t* used) {
+static int group_objective_batch_impl(sb200_group* grp, const double* coeffs, int64_t B, int32_t shard,
+                                      const sb200_batch_opts* opts, double* S, double* Amin, double* Amax, int64_t* nan,
+                                      int32_t* used) {
     if (!grp) return SB200_EINVAL;
     if (!coeffs || B < 1 || !S || !Amin || !Amax || !nan) return gfail(grp, SB200_EINVAL, "bad arguments (nbatch=%lld)", (long long)B);
     sb200_ctx* c0 = grp->members[0];
