@@ -570,6 +570,8 @@ class Optimize:
     def _start_workers(self, nstarts):
         """Spawn the SciPy worker processes for a scan of `nstarts` searches (None: the scan stays in this process)."""
         workers = self._worker_count(nstarts)
+        if workers <= 1:
+            return None
         # Spawned by default: a fresh interpreter per worker costs 0.2 s of the scan's wall time (they start while this
         # process creates its CUDA context) and is safe whatever threads the caller already runs.  Forking
         # (OPTSTENCIL_START_METHOD=fork) is honoured only while this process has not called into CUDA; the workers
@@ -579,10 +581,8 @@ class Optimize:
         if method == 'fork' and (not hasattr(os, 'fork') or _capi.cuda_touched()):
             print('optimize: not forking a process that has called into CUDA; spawning the workers instead')
             method = 'spawn'
-        if workers > 1 and method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
+        if method == 'spawn' and not hasattr(sys.modules.get('__main__'), '__file__'):
             print('optimize: worker processes need an importable __main__ (not stdin / REPL); running in-process')
-            workers = 0
-        if workers <= 1:
             return None
         import multiprocessing as mp
         mpc = mp.get_context(method)
