@@ -153,6 +153,23 @@ def test_batch_api_matches_scalar_api(es):
     np.testing.assert_array_equal(d.norm_batch(P), out["norm"])
 
 
+def test_a_batch_is_a_throughput_launch_by_its_evaluations(es):
+    """Few rows on a large grid (a rank's share of the benchmark batch) take the throughput path -- no cache warming, the
+    library picks series and screening variant -- like many rows do; small batches warm the scalar API's cache."""
+    d = es.Dispersion3D(1.0, 1.0, 12, es.StencilFree3D())
+    P = 0.05 * np.random.default_rng(8).standard_normal((6, 10))
+    P[:, 0] = 0.4
+    small = d.evaluate_batch(P)
+    assert len(d._cache) == 6
+    d2 = es.Dispersion3D(1.0, 1.0, 12, es.StencilFree3D())
+    d2.throughput_evals = 6 * 12 ** 3          # this very batch now counts as large
+    large = d2.evaluate_batch(P)
+    assert len(d2._cache) == 0 and d2.stats["launches"] == 1 and d2.stats["evaluated"] == 6
+    for k in ("stencil_ok", "dt_ok"):
+        np.testing.assert_array_equal(small[k], large[k])          # from the bit-exact extrema either way
+    assert np.max(relerr(large["norm"], small["norm"])) <= 1e-13
+
+
 def test_pickle_roundtrip_drops_the_device_handle(es):
     d = es.Dispersion2D(1.0, 25, es.StencilIsotropic2D())
     es.weight_functions["xaxis_soft"](0.4)(d)
