@@ -198,7 +198,9 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
 #pragma unroll 1
             for (int it = 0; it < nit; ++it) {
                 const int yy = (yup ? it : nit - 1 - it) * U;
-                bool pass = true;
+                // one predicate per chain (two compares each), combined afterwards: a single running predicate would
+                // string all 2 U C compares into one dependent chain (ncu: "wait" stalls at 2.6 warps per issue slot)
+                bool ok[U * C];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double* r = wrows + (size_t)min(yy + u, nrows - 1) * ROW;
@@ -207,10 +209,14 @@ __device__ __noinline__ void extrema_only_sweep(const GridDev& g, const BatchArg
                     for (int c = 0; c < C; ++c) {
                         const double2 q = *reinterpret_cast<const double2*>(r + 2 + 2 * c);
                         const double wv = fma(tzys[c], sy2r, fma(q.y, sz2r, __dadd_rn(q.x, Ts[c])));
-                        pass = pass && (wv < tmax[c]) && (wv > tmin[c]);
+                        ok[u * C + c] = (wv < tmax[c]) & (wv > tmin[c]);
                     }
                 }
-                const bool need = !pass;
+#pragma unroll
+                for (int w = 1; w < U * C; w *= 2)
+#pragma unroll
+                    for (int j = 0; j + w < U * C; j += 2 * w) ok[j] = ok[j] & ok[j + w];
+                const bool need = !ok[0];
                 if (!__any_sync(FULL, need)) continue;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
